@@ -1,0 +1,232 @@
+/*
+ * pa_b200.h -- C ABI of the B200-native global-transposition hot path.
+ *
+ * This is the drop-in boundary for the `transpose!` path of PencilArrays.jl
+ * (reference: src/Transpositions/Transpositions.jl).  The reference has no
+ * FFI of its own: its seam is Julia multiple dispatch on the array type
+ * carried by a `Pencil` (Pencils.jl:282-304).  A device array type plugs in
+ * by providing the "generic" methods `copy_range!` (Transpositions.jl:568-583),
+ * `_viewreshape` (:615-623), `_permutedims!` (:648-664) and the transport
+ * pair `transpose_send_other!` / `MPI.Alltoallv!` / `MPI.Waitany`
+ * (:462-484, :422, :513).  Each entry point below names the reference
+ * function it replaces.  `INTEGRATION.md` shows the Julia `ccall` stubs.
+ *
+ * Conventions
+ *  - plain C: opaque handles, `int64_t` sizes, `void*` device pointers,
+ *    `void*` for `cudaStream_t`; no torch / C++ types cross this boundary;
+ *  - dimension indices, permutations, ranges and peer indices are 1-BASED and
+ *    ranges are inclusive, exactly as the Julia reference passes them;
+ *  - every function returns a `pa_status`; nothing throws across the ABI.
+ *    The Julia veneer maps PA_EINVAL / PA_EINCOMPAT to `ArgumentError` and
+ *    PA_EDIM to `DimensionMismatch` (Transpositions.jl:99-103,181-198;
+ *    arrays.jl:108-114);
+ *  - there is NO CPU fallback: every data-path call fails with PA_ENOGPU /
+ *    PA_ECUDA when no device is usable.
+ */
+#ifndef PA_B200_H
+#define PA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_MAX_DIMS 8        /* spatial + extra dims of one array           */
+#define PA_MAX_TOPO 7        /* dims of the process grid (M < N)            */
+#define PA_UNIQUE_ID_BYTES 128
+
+typedef enum pa_status {
+  PA_OK = 0,
+  PA_EINVAL = 1,     /* bad argument                      -> ArgumentError      */
+  PA_EINCOMPAT = 2,  /* pencils not transposable          -> ArgumentError      */
+  PA_EDIM = 3,       /* array does not match its pencil   -> DimensionMismatch  */
+  PA_ECUDA = 4,      /* CUDA runtime error (see pa_last_error)                  */
+  PA_ENCCL = 5,      /* NCCL error / NCCL library not loadable                  */
+  PA_ENOMEM = 6,     /* device or host allocation failed                        */
+  PA_ESTATE = 7,     /* call sequence error (e.g. comm missing for Nproc > 1)   */
+  PA_ENOGPU = 8      /* no CUDA device: the data path has no CPU fallback       */
+} pa_status;
+
+typedef enum pa_method {
+  PA_POINT_TO_POINT = 0, /* Transpositions.PointToPoint  (Transpositions.jl:18) */
+  PA_ALLTOALLV = 1       /* Transpositions.Alltoallv     (Transpositions.jl:19) */
+} pa_method;
+
+/* flags of pa_transpose */
+#define PA_WAITALL   1u  /* transpose!(t; waitall=true)   (Transpositions.jl:170-176) */
+#define PA_NO_OVERLAP 2u /* run pack -> exchange -> unpack strictly in sequence      */
+#define PA_STAGE_SELF 4u /* self block through recv_buf like the reference (:393-403)
+                            instead of the fused src->dest kernel                    */
+
+typedef struct pa_topology pa_topology; /* MPITopology   (MPITopologies.jl:72-119) */
+typedef struct pa_pencil pa_pencil;     /* Pencil        (Pencils.jl:151-272)      */
+typedef struct pa_plan pa_plan;         /* Transposition (Transpositions.jl:69-119)*/
+typedef struct pa_comm pa_comm;         /* NCCL communicator standing in for
+                                           topology.comm / subcomms               */
+
+/* ---- library ------------------------------------------------------------- */
+const char* pa_version(void);
+const char* pa_strerror(pa_status s);
+/* detail text of the last failure on the calling thread ("" if none) */
+const char* pa_last_error(void);
+/* number of CUDA kernels this library has launched in this process */
+int64_t pa_launch_count(void);
+/* number of visible CUDA devices (0 on a CPU-only box); never fails */
+int pa_device_count(void);
+
+/* ---- MPITopology ---------------------------------------------------------
+ * Row-major rank grid, identical to MPI_Cart_create(reorder=false)
+ * (MPITopologies.jl:125-131,208-226): the LAST coordinate varies fastest.   */
+pa_status pa_dims_create(int nprocs, int M, int64_t* dims /* out[M] */);
+        /* balanced, non-increasing factorisation: MPI_Dims_create analogue
+           (MPITopologies.jl:138-144)                                        */
+pa_status pa_topology_create(int M, const int64_t* dims, int world_rank,
+                             pa_topology** out);
+void pa_topology_destroy(pa_topology* t);
+pa_status pa_topology_info(const pa_topology* t, int* M, int64_t* dims /*[M]*/,
+                           int* world_rank, int* world_size,
+                           int64_t* coords_local /*[M], 1-based*/);
+pa_status pa_topology_rank_of(const pa_topology* t,
+                              const int64_t* coords /*1-based*/, int* rank);
+/* world ranks of the grid line through the local coords along grid dim R
+ * (1-based) -- `subcomm_ranks[R]` + `get_remote_indices`
+ * (Transpositions.jl:293-299,539-549)                                       */
+pa_status pa_topology_line(const pa_topology* t, int R, int* ranks /*[dims[R]]*/);
+
+/* ---- Pencil -------------------------------------------------------------- */
+/* `share_with` != NULL reproduces Pencil(p; decomp_dims, permute): the new
+ * pencil shares send_buf / recv_buf with `share_with` (Pencils.jl:257-271). */
+pa_status pa_pencil_create(pa_topology* topo, int N, const int64_t* size_global,
+                           const int* decomp_dims /*[M], 1-based*/,
+                           const int* perm /*[N], 1-based; NULL = NoPermutation*/,
+                           pa_pencil* share_with, pa_pencil** out);
+void pa_pencil_destroy(pa_pencil* p);
+/* range_local / range_remote (Pencils.jl:472-497): `coords` NULL = local rank;
+ * memory_order != 0 applies the pencil's permutation. lo/hi 1-based inclusive
+ * (hi = lo - 1 for an empty range).                                          */
+pa_status pa_pencil_range(const pa_pencil* p, const int64_t* coords,
+                          int memory_order, int64_t* lo, int64_t* hi);
+pa_status pa_pencil_size_local(const pa_pencil* p, int memory_order,
+                               int64_t* dims /*[N]*/);
+/* staging arenas living in the pencil family (Pencils.jl:185-189).  Device
+ * pointers; capacity in bytes; grow-only (Transpositions.jl:313-317).       */
+pa_status pa_pencil_buffers(const pa_pencil* p, void** send_buf,
+                            int64_t* send_cap, void** recv_buf,
+                            int64_t* recv_cap);
+pa_status pa_pencil_reserve(pa_pencil* p, int64_t send_bytes, int64_t recv_bytes);
+
+/* ---- Transposition plan --------------------------------------------------
+ * Transposition(dest, src; method) (Transpositions.jl:93-118): compatibility
+ * checks (assert_compatible, :181-198), `dim` discovery (:110), per-peer
+ * ranges/offsets (transpose_send!, :380-416; transpose_recv!, :516-524), all
+ * reduced once to kernel launch descriptors.                                */
+pa_status pa_plan_create(pa_pencil* pin, pa_pencil* pout, int n_extra,
+                         const int64_t* extra_dims, int elsize, pa_method method,
+                         pa_plan** out);
+void pa_plan_destroy(pa_plan* plan);
+
+typedef struct pa_plan_info {
+  int dim;            /* grid dim of the exchange, 1-based; 0 = `nothing` (local) */
+  int nproc;          /* topology.dims[dim]  (1 when dim == 0)                  */
+  int self_index;     /* my index in the grid line, 1-based                      */
+  int same_perm;      /* local path: plain copy! (Transpositions.jl:226-227)     */
+  int elsize;
+  int method;
+  int64_t length_in;       /* length(Ai), elements incl. extra dims             */
+  int64_t length_out;      /* length(Ao)                                        */
+  int64_t length_self;     /* Transpositions.jl:302-305                         */
+  int64_t send_bytes;      /* sizeof(T) * length_send       (:308,313)          */
+  int64_t recv_bytes;      /* sizeof(T) * length_recv_total (:309,316)          */
+} pa_plan_info;
+pa_status pa_plan_get_info(const pa_plan* plan, pa_plan_info* info);
+
+typedef struct pa_peer_info {
+  int world_rank;        /* rank of peer n in the world communicator            */
+  int is_self;
+  int64_t send_offset;   /* bytes into send_buf (self: unused, 0)               */
+  int64_t send_count;    /* bytes                                               */
+  int64_t recv_offset;   /* bytes into recv_buf; self block sits at the tail
+                            (Transpositions.jl:393-403)                         */
+  int64_t recv_count;    /* bytes                                               */
+} pa_peer_info;
+pa_status pa_plan_get_peer(const pa_plan* plan, int n /*1-based*/, pa_peer_info* info);
+
+/* Strided-copy descriptor of one block as the kernels see it, exported so
+ * tests can compare the C++ plan with the oracle's independent derivation.
+ * op: 0 = pack (src parent -> contiguous), 1 = unpack (contiguous -> dest
+ * parent), 2 = fused self/local (src parent -> dest parent).
+ * Dims are listed in the source's memory order incl. merged extra dims;
+ * strides and offsets in elements.                                           */
+typedef struct pa_block_desc {
+  int nd;
+  int64_t extent[PA_MAX_DIMS];
+  int64_t src_stride[PA_MAX_DIMS];
+  int64_t dst_stride[PA_MAX_DIMS];
+  int64_t src_offset;
+  int64_t dst_offset;
+  int kernel_class;   /* 0 empty, 1 row copy, 2 tiled transpose, 3 generic scalar,
+                         4 contiguous memcpy                                     */
+  int vec_bytes;      /* access width chosen for this block                      */
+} pa_block_desc;
+pa_status pa_plan_get_block(const pa_plan* plan, int op, int n /*1-based*/,
+                            pa_block_desc* desc);
+
+/* ---- kernels (enqueue on `stream`; asynchronous) -------------------------
+ * K1 pack: copy_range! (Transpositions.jl:552-583).  `buf` is the base of
+ * send_buf (remote peer) or recv_buf (self) -- offsets come from the plan.  */
+pa_status pa_pack(pa_plan* plan, int n, const void* src, void* buf, void* stream);
+/* K2 unpack: copy_permuted! -> _viewreshape -> _permutedims! (:585-664)     */
+pa_status pa_unpack(pa_plan* plan, int n, const void* recv_buf, void* dst, void* stream);
+/* K3 fused self block: src parent -> permuted dest parent in one pass
+ * (replaces :393-403 followed by :527-529 for the local block)              */
+pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream);
+/* transpose_impl!(::Nothing) / permute_local! (:213-270).  `scratch` must hold
+ * length_out elements when src and dst alias, may be NULL otherwise.        */
+pa_status pa_permute_local(pa_plan* plan, const void* src, void* dst,
+                           void* scratch, void* stream);
+/* raw N-d strided copy used by all of the above (bench / tests)             */
+pa_status pa_box_copy(int nd, const int64_t* extent, const int64_t* src_stride,
+                      const int64_t* dst_stride, int elsize, const void* src,
+                      void* dst, void* stream, pa_block_desc* chosen /*NULL ok*/);
+
+/* ---- communicator --------------------------------------------------------
+ * Stands in for MPI.COMM_WORLD + MPI_Cart_sub sub-communicators
+ * (MPITopologies.jl:244-251): one NCCL communicator over all ranks, peers of
+ * a grid line addressed by world rank.  Bootstrap: rank 0 calls
+ * pa_comm_unique_id and distributes the 128 bytes by any side channel.      */
+pa_status pa_comm_unique_id(void* id128);
+pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** out);
+void pa_comm_destroy(pa_comm* c);
+
+/* ---- transpose! ----------------------------------------------------------
+ * transpose!(t; waitall) (Transpositions.jl:170-179) for device arrays.
+ * Ordered after prior work on `stream`; on return, later work on `stream`
+ * sees `dst` complete.  Without PA_WAITALL the send side (send_buf reuse) is
+ * only guaranteed after pa_wait -- MPI.Waitall(t) (:127-130).
+ * `comm` may be NULL when nproc == 1.                                        */
+pa_status pa_transpose(pa_plan* plan, pa_comm* comm, const void* src, void* dst,
+                       unsigned flags, void* stream);
+pa_status pa_wait(pa_plan* plan, void* stream);
+/* same, with HOST arrays: H2D of `src`, transpose!, D2H of `dst`; blocks until
+ * `host_dst` is valid.  Device staging is owned by the plan.                 */
+pa_status pa_transpose_host(pa_plan* plan, pa_comm* comm, const void* host_src,
+                            void* host_dst, unsigned flags);
+
+/* CUDA-event timings (ms) of the last pa_transpose on this plan, named after
+ * the reference's TimerOutputs sections (Transpositions.jl:172-175,326,336).
+ * Blocks until that transpose has finished.                                  */
+typedef struct pa_timings {
+  float total_ms;        /* "transpose!"    */
+  float pack_ms;         /* "pack data"     */
+  float exchange_ms;     /* Isend/Irecv or "MPI.Alltoallv!" */
+  float unpack_ms;       /* "unpack data"   */
+} pa_timings;
+pa_status pa_plan_timings(pa_plan* plan, pa_timings* t);
+pa_status pa_plan_enable_timing(pa_plan* plan, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PA_B200_H */

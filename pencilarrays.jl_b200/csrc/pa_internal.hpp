@@ -1,0 +1,164 @@
+// Internal structures of libpa_b200: geometry, plan, kernel descriptors.
+// Everything here is host-side integer arithmetic; indices are 0-BASED and
+// ranges half-open [lo, hi) internally (the C ABI converts from/to Julia's
+// 1-based inclusive convention).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pa_b200.h"
+
+namespace pa {
+
+using i64 = int64_t;
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+// ---- MPITopology (MPITopologies.jl:72-119) ---------------------------------
+struct Topology {
+  int M = 0;
+  i64 dims[PA_MAX_TOPO] = {0};
+  int rank = 0;
+  int size = 1;
+  i64 coords[PA_MAX_TOPO] = {0};  // 0-based coords of `rank`
+
+  // rank <-> coords, row-major (last coordinate fastest):
+  // MPI_Cart_create(reorder=false), MPITopologies.jl:125-131,208-226
+  void coords_of(int r, i64* c) const;
+  int rank_of(const i64* c) const;
+  bool same_as(const Topology& o) const;
+};
+
+// ---- staging arenas shared by a pencil family (Pencils.jl:185-189,265-270) -
+struct Buffers {
+  void* send = nullptr;
+  i64 send_cap = 0;
+  void* recv = nullptr;
+  i64 recv_cap = 0;
+  void* comm_done_event = nullptr;  // cudaEvent_t of the last exchange using them
+  ~Buffers();
+  pa_status reserve(i64 send_bytes, i64 recv_bytes);
+};
+
+// ---- Pencil (Pencils.jl:151-272) -------------------------------------------
+struct Pencil {
+  std::shared_ptr<Topology> topo;
+  int N = 0;
+  i64 size_global[PA_MAX_DIMS] = {0};
+  int decomp[PA_MAX_TOPO] = {0};  // 0-based array dim decomposed by grid dim i
+  int perm[PA_MAX_DIMS] = {0};    // 0-based; memory dim i holds logical dim perm[i]
+  bool perm_identity = true;
+  std::shared_ptr<Buffers> bufs;
+
+  // axes_all[coords] in logical order (data_ranges.jl:4-9,30-45)
+  void range_of(const i64* coords, i64* lo, i64* hi) const;
+  void range_local(i64* lo, i64* hi) const { range_of(topo->coords, lo, hi); }
+};
+
+// block partition rule, 0-based half-open restatement of
+// local_data_range(p, P, N) = (N(p-1))÷P + 1 : (N p)÷P   (data_ranges.jl:4-9)
+inline void local_data_range(i64 p0, i64 P, i64 N, i64* lo, i64* hi) {
+  *lo = (N * p0) / P;
+  *hi = (N * (p0 + 1)) / P;
+}
+
+// ---- strided box copy: the one primitive all kernels implement -------------
+struct Dim {
+  i64 e;   // extent (elements)
+  i64 ss;  // source stride (elements)
+  i64 ds;  // destination stride (elements)
+};
+
+enum KernelClass { KC_EMPTY = 0, KC_ROWS = 1, KC_TRANSPOSE = 2, KC_TILE_SCALAR = 3 };
+
+// Canonical, launch-ready description of `dst[off_d + sum k_i ds_i] =
+// src[off_s + sum k_i ss_i]` for k in the box.  dims[0] = X (smallest source
+// stride), dims[1] = Y (the tile's second dim), the rest are outer dims.
+struct BlockCopy {
+  // as given (source memory order), kept for pa_plan_get_block
+  int nd_raw = 0;
+  Dim raw[PA_MAX_DIMS];
+  i64 src_off = 0, dst_off = 0;  // elements
+  int elsize = 0;
+  i64 count = 0;                 // elements in the box
+
+  // canonical form
+  int nd = 0;
+  Dim d[PA_MAX_DIMS];
+  int klass = KC_EMPTY;
+  int stride_align = 16;  // largest power of two (<=16) dividing every byte stride / run length
+  bool contiguous_both = false;  // whole block is one contiguous run on both sides
+};
+
+void canonicalize(BlockCopy& b);
+
+// launch on `stream`; src/dst are array base pointers (offsets come from b)
+pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* stream,
+                       int* vec_used);
+
+// ---- Transposition plan (Transpositions.jl:69-119, 281-343) ----------------
+struct Peer {
+  int world_rank = -1;
+  bool is_self = false;
+  i64 send_off = 0, send_cnt = 0;  // elements
+  i64 recv_off = 0, recv_cnt = 0;  // elements
+  BlockCopy pack;    // K1: src parent box -> contiguous @ (send_off | recv_off)
+  BlockCopy unpack;  // K2: contiguous @ recv_off -> dest parent box
+};
+
+struct TransposeState;  // streams/events, defined in transpose.cpp
+
+struct Plan {
+  std::shared_ptr<Pencil> pin, pout;
+  int n_extra = 0;
+  i64 extra[PA_MAX_DIMS] = {0};
+  i64 prod_extra = 1;
+  int elsize = 0;
+  int method = PA_POINT_TO_POINT;
+  int dim = -1;  // grid dim of the exchange (0-based), -1 = local only
+  int nproc = 1;
+  int self_index = 0;  // 0-based
+  bool same_perm = false;
+  i64 length_in = 0, length_out = 0, length_self = 0;
+  i64 send_elems = 0, recv_elems = 0;
+  std::vector<Peer> peers;
+  BlockCopy self_fused;  // K3: src parent -> dest parent (self block or local permute)
+  TransposeState* st = nullptr;
+  // host-transpose staging
+  void* h_src_dev = nullptr;
+  void* h_dst_dev = nullptr;
+  ~Plan();
+};
+
+pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, int n_extra,
+                     const i64* extra, int elsize, int method, Plan** out);
+
+// ---- communicator ----------------------------------------------------------
+struct Comm;
+pa_status comm_unique_id(void* id128);
+pa_status comm_init(const void* id128, int nranks, int rank, Comm** out);
+void comm_destroy(Comm* c);
+
+pa_status transpose(Plan* plan, Comm* comm, const void* src, void* dst, unsigned flags,
+                    void* stream);
+pa_status wait_sends(Plan* plan, void* stream);
+pa_status permute_local(Plan* plan, const void* src, void* dst, void* scratch, void* stream);
+pa_status transpose_host(Plan* plan, Comm* comm, const void* hsrc, void* hdst, unsigned flags);
+pa_status plan_timings(Plan* plan, pa_timings* t);
+pa_status plan_enable_timing(Plan* plan, int on);
+void destroy_state(TransposeState* st);
+
+int device_count();
+i64 launch_count();
+
+}  // namespace pa
+
+struct pa_topology { std::shared_ptr<pa::Topology> p; };
+struct pa_pencil { std::shared_ptr<pa::Pencil> p; };
+struct pa_plan { pa::Plan* p; };
+struct pa_comm { pa::Comm* p; };

@@ -1,0 +1,152 @@
+"""``Transpositions``: the reference module's public surface
+(src/Transpositions/Transpositions.jl) over libpa_b200.
+
+    t = Transposition(dest, src; method=PointToPoint())   # :93-118
+    transpose_(t; waitall=True)                           # transpose!(t; waitall)   :170-179
+    Waitall(t)                                            # MPI.Waitall(t)           :127-130
+    transpose_(dest, src; method=...)                     # transpose!(dest, src)    :160-168
+
+Python has no ``!`` in identifiers: ``transpose_`` (torch's in-place naming)
+stands for ``transpose!``; ``transpose_bang`` is an alias.  Errors follow the
+reference: incompatible pencils / extra dims raise ``ArgumentError``.
+
+All work is enqueued on the CURRENT torch CUDA stream and is asynchronous with
+respect to the host, like any other CUDA op.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, i64arr, ArgumentError, PlanInfo, PeerInfo, Timings
+from .arrays import PencilArray
+from .pencils import Pencil
+
+
+class AbstractTransposeMethod:
+    def __repr__(self):
+        return type(self).__name__
+
+    def __eq__(self, other):
+        return type(self) is type(other)
+
+    def __hash__(self):
+        return hash(type(self).__name__)
+
+
+class PointToPoint(AbstractTransposeMethod):  # Transpositions.jl:18
+    code = _lib.PA_POINT_TO_POINT
+
+
+class Alltoallv(AbstractTransposeMethod):  # Transpositions.jl:19
+    code = _lib.PA_ALLTOALLV
+
+
+class _Plan:
+    """Owner of one ``pa_plan`` handle (geometry + launch descriptors + streams)."""
+
+    def __init__(self, pin: Pencil, pout: Pencil, extra_dims, elsize: int, method):
+        h = C.c_void_p()
+        check(lib.pa_plan_create(pin._h, pout._h, len(extra_dims), i64arr(extra_dims), elsize,
+                                 method.code, C.byref(h)))
+        self.h = h
+        info = PlanInfo()
+        check(lib.pa_plan_get_info(h, C.byref(info)))
+        self.info = info
+
+    def __del__(self):
+        try:
+            lib.pa_plan_destroy(self.h)
+        except Exception:
+            pass
+
+    def peer(self, n: int) -> PeerInfo:
+        p = PeerInfo()
+        check(lib.pa_plan_get_peer(self.h, n, C.byref(p)))
+        return p
+
+    def block(self, op: int, n: int = 1):
+        d = _lib.BlockDesc()
+        check(lib.pa_plan_get_block(self.h, op, n, C.byref(d)))
+        return d
+
+
+def _get_plan(pin: Pencil, pout: Pencil, extra_dims, elsize, method) -> _Plan:
+    # plans are cached on the output pencil: `transpose!(dest, src)` builds a
+    # fresh Transposition per call in the reference (:165); re-deriving the
+    # geometry is cheap there, re-creating streams/events per call is not here.
+    key = (id(pin), tuple(extra_dims), int(elsize), method.code)
+    hit = pout._plans.get(key)
+    if hit is not None and hit[0] is pin:
+        return hit[1]
+    plan = _Plan(pin, pout, extra_dims, elsize, method)
+    pout._plans[key] = (pin, plan)
+    return plan
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Transposition:
+    """Holds data for transposition between two pencil configurations (:69-119)."""
+
+    def __init__(self, Ao: PencilArray, Ai: PencilArray, *, method=None):
+        method = PointToPoint() if method is None else method
+        Pi, Po = Ai.pencil, Ao.pencil
+        if Ai.extra_dims != Ao.extra_dims:  # :99-103
+            raise ArgumentError(_lib.PA_EINVAL,
+                                "incompatible number of extra dimensions of PencilArrays: "
+                                f"{Ai.extra_dims} != {Ao.extra_dims}")
+        if Ai.dtype != Ao.dtype:  # PencilArray{T,N} for both arguments
+            raise ArgumentError(_lib.PA_EINVAL, f"element types differ: {Ai.dtype} != {Ao.dtype}")
+        if Pi.topology is not Po.topology:  # assert_compatible uses `!==` (:182-184)
+            raise ArgumentError(_lib.PA_EINCOMPAT, "pencil topologies must be the same.")
+        self.Pi, self.Po, self.Ai, self.Ao = Pi, Po, Ai, Ao
+        self.method = method
+        self._plan = _get_plan(Pi, Po, Ai.extra_dims, Ai.elsize, method)  # remaining checks in C
+        d = self._plan.info.dim
+        self.dim = None if d == 0 else d  # :110
+
+    @property
+    def plan(self) -> _Plan:
+        return self._plan
+
+    def timings(self) -> Timings:
+        t = Timings()
+        check(lib.pa_plan_timings(self._plan.h, C.byref(t)))
+        return t
+
+    def enable_timing(self, on=True):
+        check(lib.pa_plan_enable_timing(self._plan.h, 1 if on else 0))
+
+
+def Waitall(t: Transposition):
+    """``MPI.Waitall(t::Transposition)`` (:127-130): sends done => send_buf reusable."""
+    check(lib.pa_wait(t.plan.h, _stream_ptr()))
+    return None
+
+
+def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False):
+    """``transpose!(dest, src; method)`` or ``transpose!(t; waitall)`` (:160-179)."""
+    if len(args) == 1 and isinstance(args[0], Transposition):
+        t = args[0]
+    elif len(args) == 2:
+        dest, src = args
+        if dest is src:  # same pencil & same data (:164)
+            return dest
+        t = Transposition(dest, src, method=method)
+        waitall = True
+    else:
+        raise TypeError("transpose_(dest, src; method) or transpose_(t; waitall)")
+    flags = (_lib.PA_WAITALL if waitall else 0) | (0 if overlap else _lib.PA_NO_OVERLAP) | (
+        _lib.PA_STAGE_SELF if stage_self else 0)
+    comm = t.Pi.topology.comm.handle
+    check(lib.pa_transpose(t.plan.h, comm, C.c_void_p(t.Ai.data_ptr()),
+                           C.c_void_p(t.Ao.data_ptr()), flags, _stream_ptr()))
+    return t if len(args) == 1 else args[0]
+
+
+transpose_bang = transpose_

@@ -1,0 +1,98 @@
+"""The C++ planner (libpa_b200: geometry, wire layout, kernel descriptors)
+against the oracle, on CPU: the descriptors are interpreted with NumPy
+(tests/util.apply_block) and every buffer must match the oracle bit for bit --
+send_buf / recv_buf wire layout (Transpositions.jl:380-416) included."""
+import math
+
+import numpy as np
+import pytest
+
+import pencilarrays_b200 as pa
+from pencilarrays_b200.transpositions import _Plan
+from oracle import pencil_oracle as O
+from util import CASES, DTYPES, beq, build_chain, emulate_transpose_with_descriptors
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+@pytest.mark.parametrize("method", [pa.PointToPoint(), pa.Alltoallv()], ids=["p2p", "a2av"])
+def test_chain_matches_oracle(case, method):
+    dtype = DTYPES[case["it"]]
+    extra = case["extra"]
+    ranks, steps = build_chain(case)
+    g = O.global_pattern(case["dims"], extra, case["it"])
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], extra, dtype)
+    G = O.gather(cur_o)
+    cur = [a.data.reshape(-1, order="F").copy() for a in cur_o]
+    for k in range(1, len(steps)):
+        pin, pout = steps[k - 1], steps[k]
+        # oracle
+        nxt_o = [O.OArray.undef(dtype, po, *extra) for (_, po) in pout]
+        states = O.transpose_all(nxt_o, cur_o, keep_states=True)
+        assert beq(O.gather(nxt_o), G)  # the reference's own check (test/transpose.jl:6-22)
+        # C planner, descriptors interpreted by NumPy
+        plans = [_Plan(pin[r][0], pout[r][0], extra, case["it"], method) for r in range(len(ranks))]
+        nxt = [np.zeros(max(1, a.data.size), dtype=dtype) for a in nxt_o]
+        sends, recvs = emulate_transpose_with_descriptors(plans, cur, nxt, dtype)
+        for r in range(len(ranks)):
+            assert beq(nxt[r][:nxt_o[r].data.size], nxt_o[r].data.reshape(-1, order="F")), (k, r)
+            info = plans[r].info
+            assert info.length_in == cur_o[r].data.size and info.length_out == nxt_o[r].data.size
+            if states is not None:  # wire layout
+                st = states[r]
+                ns, nr = info.send_bytes // case["it"], info.recv_bytes // case["it"]
+                assert beq(sends[r][:ns], st.send_buf[:ns]), ("send_buf", k, r)
+                assert beq(recvs[r][:nr], st.recv_buf[:nr]), ("recv_buf", k, r)
+                assert info.dim == O.transposition_dim(pin[r][1], pout[r][1])
+            else:
+                assert info.dim == 0
+        cur_o, cur = nxt_o, [a[:o.data.size].copy() for a, o in zip(nxt, nxt_o)]
+
+
+def test_fused_self_block_equals_pack_then_unpack():
+    """K3 (src -> dest in one pass) must equal pack-to-recv_buf + unpack for the self block."""
+    case = CASES[0]
+    dtype = DTYPES[case["it"]]
+    ranks, steps = build_chain(case)
+    g = O.global_pattern(case["dims"], (), case["it"])
+    src_o = O.scatter(g, [po for (_, po) in steps[0]], (), dtype)
+    for r in range(len(ranks)):
+        plan = _Plan(steps[0][r][0], steps[1][r][0], (), case["it"], pa.PointToPoint())
+        n_out = plan.info.length_out
+        src = src_o[r].data.reshape(-1, order="F")
+        from util import apply_block
+        a = np.zeros(n_out, dtype=dtype)
+        b = np.zeros(n_out, dtype=dtype)
+        recv = np.zeros(plan.info.recv_bytes // case["it"], dtype=dtype)
+        me = plan.info.self_index
+        apply_block(plan.block(0, me), src, recv)
+        apply_block(plan.block(1, me), recv, a)
+        apply_block(plan.block(2), src, b)
+        assert beq(a, b)
+
+
+def test_counts_are_symmetric():
+    """send count r->q equals recv count q<-r for every pair (what Isend/Irecv rely on)."""
+    for case in CASES:
+        ranks, steps = build_chain(case)
+        for k in range(1, len(steps)):
+            plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], case["extra"], case["it"],
+                           pa.PointToPoint()) for r in range(len(ranks))]
+            if plans[0].info.dim == 0:
+                continue
+            for r, pl in enumerate(plans):
+                tot_s = tot_r = 0
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if peer.is_self:
+                        assert peer.world_rank == r
+                        assert peer.recv_offset + peer.recv_count == pl.info.recv_bytes
+                        continue
+                    tot_s += peer.send_count
+                    tot_r += peer.recv_count
+                    q = plans[peer.world_rank]
+                    back = [q.peer(pp) for pp in range(1, q.info.nproc + 1)]
+                    back = [b for b in back if b.world_rank == r][0]
+                    assert back.recv_count == peer.send_count
+                    assert back.send_count == peer.recv_count
+                assert tot_s == pl.info.send_bytes
+                assert tot_r + pl.info.length_self * case["it"] == pl.info.recv_bytes
