@@ -1,0 +1,145 @@
+"""Worker for the multi-process tests; launched with torch.distributed.run.
+
+  mode "nccl": real path -- pa.transpose_ over NCCL, one GPU per rank;
+  mode "gloo": CPU box -- the C planner's descriptors are interpreted with
+               NumPy (tests/util.apply_block) and the exchange follows the
+               plan's peer table over gloo send/recv.  Checks the N>1 host
+               logic (rank grid, peer table, counts, offsets) across real
+               processes.
+Every rank recomputes the whole oracle (sizes are small) and compares its own
+part bit for bit.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+
+import pencilarrays_b200 as pa  # noqa: E402
+from pencilarrays_b200.transpositions import _Plan  # noqa: E402
+from oracle import pencil_oracle as O  # noqa: E402
+from util import CASES, DTYPES, beq, perm_of, apply_block  # noqa: E402
+import math  # noqa: E402
+
+
+def gloo_transpose(plan, src, dtype, it, rank):
+    info = plan.info
+    dst = np.zeros(max(1, info.length_out), dtype=dtype)
+    if info.dim == 0:
+        apply_block(plan.block(2), src, dst)
+        return dst
+    send = np.zeros(max(1, info.send_bytes // it), dtype=dtype)
+    recv = np.zeros(max(1, info.recv_bytes // it), dtype=dtype)
+    nproc, me = info.nproc, info.self_index
+    for p in range(1, nproc + 1):
+        peer = plan.peer(p)
+        apply_block(plan.block(0, p), src, recv if peer.is_self else send)
+    reqs, keep = [], []
+    for k in range(1, nproc):  # same rotation as the CUDA driver
+        to = plan.peer((me - 1 + k) % nproc + 1)
+        fr = plan.peer((me - 1 - k) % nproc + 1)
+        if to.send_count:
+            t = torch.from_numpy(send[to.send_offset // it:(to.send_offset + to.send_count) // it]
+                                 .view(np.uint8).copy())
+            keep.append(t)
+            reqs.append(dist.isend(t, to.world_rank))
+        if fr.recv_count:
+            t = torch.empty(fr.recv_count, dtype=torch.uint8)
+            keep.append((t, fr))
+            reqs.append(dist.irecv(t, fr.world_rank))
+    for r in reqs:
+        r.wait()
+    for item in keep:
+        if isinstance(item, tuple):
+            t, fr = item
+            recv[fr.recv_offset // it:(fr.recv_offset + fr.recv_count) // it] = t.numpy().view(dtype)
+    for p in range(1, nproc + 1):
+        apply_block(plan.block(1, p), recv, dst)
+    return dst
+
+
+def main():
+    mode = sys.argv[1]
+    if mode == "nccl":
+        comm = pa.comm_world()
+    else:
+        dist.init_process_group("gloo")
+        comm = pa.Comm(dist.get_rank(), dist.get_world_size())
+    rank, world = comm.rank, comm.size
+    ran = 0
+    for case in CASES:
+        if math.prod(case["grid"]) != world:
+            continue
+        ran += 1
+        dtype, it, extra = DTYPES[case["it"]], case["it"], case["extra"]
+        topo = pa.MPITopology(comm, case["grid"])
+        opens = [[O.OPencil(O.OTopology(case["grid"], r), case["dims"], d, p) for r in range(world)]
+                 for (d, p) in case["chain"]]
+        pens = []
+        for i, (d, p) in enumerate(case["chain"]):
+            pens.append(pa.Pencil(topo, case["dims"], d, permute=perm_of(p)) if i == 0 else
+                        pa.Pencil(pens[0], decomp_dims=d, permute=perm_of(p)))
+        g = O.global_pattern(case["dims"], extra, it)
+        cur_o = O.scatter(g, opens[0], extra, dtype)
+        variants = [(pa.PointToPoint(), True, True), (pa.PointToPoint(), False, True),
+                    (pa.Alltoallv(), True, True), (pa.PointToPoint(), True, False)]
+        if mode == "gloo":
+            cur = cur_o[rank].data.reshape(-1, order="F").copy()
+        else:
+            tdt = {4: torch.float32, 8: torch.float64, 16: torch.complex128, 2: torch.int16}[it]
+            cur = pa.PencilArray.undef(tdt, pens[0], *extra)
+            cur.data.view(torch.uint8).reshape(-1).copy_(torch.from_numpy(
+                np.ascontiguousarray(cur_o[rank].data.reshape(-1, order="F")).view(np.uint8).copy()))
+        for k in range(1, len(case["chain"])):
+            nxt_o = [O.OArray.undef(dtype, po, *extra) for po in opens[k]]
+            O.transpose_all(nxt_o, cur_o)
+            want = np.ascontiguousarray(nxt_o[rank].data.reshape(-1, order="F"))
+            if mode == "gloo":
+                plan = _Plan(pens[k - 1], pens[k], extra, it, pa.PointToPoint())
+                got = gloo_transpose(plan, cur, dtype, it, rank)[:want.size]
+                assert beq(got, want), (case["name"], k, rank)
+                cur = got
+            else:
+                nxt = None
+                for (method, overlap, waitall) in variants:
+                    nxt = pa.PencilArray.undef(tdt, pens[k], *extra)
+                    nxt.data.view(torch.uint8).fill_(0x5A)
+                    t = pa.Transposition(nxt, cur, method=method)
+                    pa.transpose_(t, waitall=waitall, overlap=overlap)
+                    if not waitall:
+                        pa.Waitall(t)
+                    torch.cuda.synchronize()
+                    got = nxt.data.view(torch.uint8).reshape(-1).cpu().numpy()
+                    assert got.tobytes() == want.view(np.uint8).tobytes(), \
+                        (case["name"], k, rank, method, overlap, waitall)
+                cur = nxt
+            cur_o = nxt_o
+        if mode == "nccl" and len(case["chain"]) >= 3 and not extra:
+            # in place: ManyPencilArray over the first three pencils (test/pencils.jl:224-239)
+            A = pa.ManyPencilArray(tdt, *pens[:3])
+            o0 = O.scatter(g, opens[0], extra, dtype)
+            A[1].data.view(torch.uint8).reshape(-1).copy_(torch.from_numpy(
+                np.ascontiguousarray(o0[rank].data.reshape(-1, order="F")).view(np.uint8).copy()))
+            o1 = [O.OArray.undef(dtype, po) for po in opens[1]]
+            O.transpose_all(o1, o0)
+            o2 = [O.OArray.undef(dtype, po) for po in opens[2]]
+            O.transpose_all(o2, o1)
+            pa.transpose_(A[2], A[1])
+            pa.transpose_(A[3], A[2])
+            torch.cuda.synchronize()
+            got = A[3].data.view(torch.uint8).reshape(-1).cpu().numpy()
+            want = np.ascontiguousarray(o2[rank].data.reshape(-1, order="F")).view(np.uint8)
+            assert got.tobytes() == want.tobytes(), ("inplace", case["name"], rank)
+    dist.barrier()
+    if rank == 0:
+        print(f"MP_WORKER_OK mode={mode} world={world} cases={ran} launches={pa.launch_count()}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,15 @@ CASES = [
     # ComplexF64 with PencilFFTs' usual permutations, 16-byte vectors
     dict(name="c128_fft_perms", grid=(2, 2), dims=(8, 12, 10), extra=(), it=16,
          chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1))]),
+    # 2-rank variants (what a 2-GPU box can run with real NCCL)
+    dict(name="two_ranks_1x2", grid=(1, 2), dims=(16, 21, 41), extra=(), it=8,
+         chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 2, 1)), ((1, 3), (2, 3, 1)),
+                ((2, 3), None)]),
+    dict(name="two_ranks_2x1", grid=(2, 1), dims=(16, 21, 41), extra=(2,), it=16,
+         chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1)), ((1, 3), (2, 1, 3)),
+                ((2, 3), None)]),
+    dict(name="two_ranks_slab", grid=(2,), dims=(20, 16, 4), extra=(), it=4,
+         chain=[((1,), None), ((2,), (2, 3, 1)), ((2,), (3, 2, 1)), ((3,), None)]),
     # 2-byte elements, extra dim, 4-D data
     dict(name="u16_4d", grid=(2, 2), dims=(6, 5, 4, 7), extra=(2,), it=2,
          chain=[((3, 4), None), ((1, 4), (4, 3, 2, 1)), ((1, 2), (3, 4, 1, 2))]),
