@@ -75,6 +75,9 @@ const char* pa_last_error(void);
 int64_t pa_launch_count(void);
 /* number of visible CUDA devices (0 on a CPU-only box); never fails */
 int pa_device_count(void);
+/* bind the calling thread to a device (one process per GPU: LOCAL_RANK).  All
+ * handles created afterwards (streams, staging arenas, communicator) live there. */
+pa_status pa_set_device(int device);
 
 /* ---- MPITopology ---------------------------------------------------------
  * Row-major rank grid, identical to MPI_Cart_create(reorder=false)

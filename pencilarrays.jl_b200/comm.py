@@ -73,6 +73,7 @@ def comm_world(init_nccl: bool | None = None) -> Comm:
     if init_nccl:
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", str(rank % max(1, torch.cuda.device_count())))))
         torch.cuda.current_stream().synchronize()  # make sure the primary context exists
+        check(lib.pa_set_device(torch.cuda.current_device()))
         buf = C.create_string_buffer(_lib.PA_UNIQUE_ID_BYTES)
         if rank == 0:
             check(lib.pa_comm_unique_id(buf))

@@ -40,6 +40,13 @@ const char* pa_strerror(pa_status s) {
 const char* pa_last_error(void) { return last_error(); }
 int64_t pa_launch_count(void) { return launch_count(); }
 int pa_device_count(void) { return device_count(); }
+pa_status pa_set_device(int device) {
+  if (device_count() == 0) {
+    set_error("no CUDA device");
+    return PA_ENOGPU;
+  }
+  return set_device(device);
+}
 
 // ---- topology -----------------------------------------------------------------
 pa_status pa_dims_create(int nprocs, int M, int64_t* dims) {

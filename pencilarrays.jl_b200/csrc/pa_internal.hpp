@@ -154,6 +154,7 @@ pa_status plan_enable_timing(Plan* plan, int on);
 void destroy_state(TransposeState* st);
 
 int device_count();
+pa_status set_device(int dev);
 i64 launch_count();
 
 }  // namespace pa

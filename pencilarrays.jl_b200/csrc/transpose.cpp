@@ -36,6 +36,11 @@ namespace pa {
     }                                                                             \
   } while (0)
 
+pa_status set_device(int dev) {
+  CU(cudaSetDevice(dev));
+  return PA_OK;
+}
+
 // ---- NCCL via dlopen ---------------------------------------------------------
 struct NcclApi {
   void* h = nullptr;

@@ -16,6 +16,7 @@ respect to the host, like any other CUDA op.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import torch
 
@@ -86,7 +87,15 @@ def _get_plan(pin: Pencil, pout: Pencil, extra_dims, elsize, method) -> _Plan:
     return plan
 
 
+_bound = threading.local()
+
+
 def _stream_ptr():
+    # keep the library's (statically linked) CUDA runtime on torch's current device
+    dev = torch.cuda.current_device()
+    if getattr(_bound, "dev", None) != dev:
+        check(lib.pa_set_device(dev))
+        _bound.dev = dev
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -24,6 +24,7 @@ def host_bytes(t: torch.Tensor) -> np.ndarray:
 
 
 def stream_ptr():
+    check(lib.pa_set_device(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
