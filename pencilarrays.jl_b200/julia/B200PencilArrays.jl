@@ -1,0 +1,177 @@
+# B200PencilArrays.jl -- Julia veneer over libpa_b200 (include/pa_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia (and no
+# MPI).  The same C ABI is exercised call-for-call by the Python/ctypes host
+# mirror and its tests; this file is the binding a PencilArrays.jl maintainer
+# would load next to CUDA.jl.  It plugs in at the reference's own seam --
+# multiple dispatch on the array type carried by the `Pencil`
+# (Pencils.jl:282-304) -- in two ways:
+#
+#   (A) kernel level: the "generic array" methods of the hot path
+#       copy_range!   (Transpositions.jl:568-583)  -> pa_box_copy (K1, no allocation)
+#       _permutedims! (Transpositions.jl:648-664)  -> pa_box_copy (K2, ONE pass, no temp)
+#       so that the reference's own transpose_send!/transpose_recv! loops and a
+#       CUDA-aware MPI keep driving the exchange;
+#   (B) whole path: transpose!(t::Transposition; waitall) (Transpositions.jl:170-179)
+#       -> pa_transpose (pack / NCCL exchange / unpack pipelined on CUDA streams),
+#       MPI.Waitall(t) -> pa_wait.
+module B200PencilArrays
+
+using PencilArrays
+using PencilArrays: Pencils, Transpositions, MemoryOrder, LogicalOrder
+using PencilArrays.Transpositions: Transposition, PointToPoint, Alltoallv, AbstractTransposeMethod
+using StaticPermutations
+using CUDA
+import MPI
+
+const libpa = get(ENV, "PA_B200_LIB", "libpa_b200.so")
+
+# ---- status -> exception (pa_b200.h: pa_status) ------------------------------
+function check(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:pa_last_error, libpa), Cstring, ()))
+    what = unsafe_string(ccall((:pa_strerror, libpa), Cstring, (Cint,), status))
+    status in (1, 2) && throw(ArgumentError("$what: $msg"))       # PA_EINVAL, PA_EINCOMPAT
+    status == 3 && throw(DimensionMismatch("$what: $msg"))        # PA_EDIM
+    error("libpa_b200: $what: $msg")
+end
+
+stream_ptr() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
+devptr(x::CuArray) = reinterpret(Ptr{Cvoid}, pointer(x))
+
+# ---- (A) kernel-level overrides ------------------------------------------------
+# column-major strides (in elements) of dims
+function colstrides(dims::NTuple{N,Int}) where {N}
+    s = ones(Int64, N)
+    for i in 2:N
+        s[i] = s[i - 1] * dims[i - 1]
+    end
+    s
+end
+
+# pack: strided sub-box of the memory-order parent -> contiguous send/recv buffer
+function Transpositions.copy_range!(
+        dest::CuVector{T}, dest_offset::Integer,
+        src::PencilArray{T,N,<:CuArray}, src_range_memorder::NTuple,
+    ) where {T,N}
+    src_p = parent(src)
+    exdims = extra_dims(src)
+    ranges = (src_range_memorder..., map(Base.OneTo, exdims)...)
+    ext = Int64[length(r) for r in ranges]
+    sstr = colstrides(size(src_p))
+    dstr = colstrides(Tuple(ext))
+    soff = sum((first(r) - 1) * s for (r, s) in zip(ranges, sstr))
+    check(ccall((:pa_box_copy, libpa), Cint,
+        (Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        length(ext), ext, sstr, dstr, sizeof(T),
+        devptr(src_p) + soff * sizeof(T), devptr(dest) + dest_offset * sizeof(T),
+        stream_ptr(), C_NULL))
+    dest
+end
+
+# unpack: dense block (dims in Pi memory order) -> permuted sub-box of parent(dst),
+# one pass, no temporary (the reference allocates `tmp` and copies twice, :659-661)
+function Transpositions._permutedims!(
+        ::Type{<:CuArray}, v::SubArray{T,N,<:CuArray}, src::CuArray{T,N}, perm,
+    ) where {T,N}
+    E = N - length(perm)
+    pperm = Tuple(append(perm, Val(E)))          # v[k] = src[j], k[i] = j[pperm[i]]
+    ext = Int64[size(src)...]
+    sstr = colstrides(size(src))
+    pstr = colstrides(size(parent(v)))
+    dstr = zeros(Int64, N)
+    for i in 1:N
+        dstr[pperm[i]] = pstr[i]
+    end
+    doff = sum((first(r) - 1) * s for (r, s) in zip(parentindices(v), pstr))
+    check(ccall((:pa_box_copy, libpa), Cint,
+        (Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        N, ext, sstr, dstr, sizeof(T), devptr(src), devptr(parent(v)) + doff * sizeof(T),
+        stream_ptr(), C_NULL))
+    v
+end
+
+# ---- (B) whole-path override ------------------------------------------------------
+mutable struct Handles
+    topo::Ptr{Cvoid}
+    pencils::IdDict{Any,Ptr{Cvoid}}
+    plans::Dict{Any,Ptr{Cvoid}}
+    comm::Ptr{Cvoid}
+end
+const HANDLES = IdDict{Any,Handles}()   # keyed by MPITopology (identity, like `!==` at :182)
+
+function handles(topo)
+    get!(HANDLES, topo) do
+        dims = Int64[size(topo)...]
+        rank = MPI.Comm_rank(get_comm(topo))
+        h = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_topology_create, libpa), Cint, (Cint, Ptr{Int64}, Cint, Ptr{Ptr{Cvoid}}),
+                    length(dims), dims, rank, h))
+        # NCCL bootstrap over the MPI communicator the user already has
+        id = zeros(UInt8, 128)
+        rank == 0 && check(ccall((:pa_comm_unique_id, libpa), Cint, (Ptr{UInt8},), id))
+        MPI.Bcast!(id, 0, get_comm(topo))
+        c = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_set_device, libpa), Cint, (Cint,), CUDA.deviceid(CUDA.device())))
+        check(ccall((:pa_comm_init_rank, libpa), Cint, (Ptr{UInt8}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                    id, MPI.Comm_size(get_comm(topo)), rank, c))
+        Handles(h[], IdDict{Any,Ptr{Cvoid}}(), Dict{Any,Ptr{Cvoid}}(), c[])
+    end
+end
+
+function pencil_handle(H::Handles, p::Pencil{N}) where {N}
+    get!(H.pencils, p) do
+        perm = permutation(p)
+        permv = isidentity(perm) ? C_NULL : Cint[Tuple(perm)...]
+        # pencils sharing send_buf (Pencils.jl:265-270) share the device arenas
+        share = C_NULL
+        for (q, hq) in H.pencils
+            q.send_buf === p.send_buf && (share = hq; break)
+        end
+        h = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_pencil_create, libpa), Cint,
+            (Ptr{Cvoid}, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Cint}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+            H.topo, N, Int64[size_global(p)...], Cint[decomposition(p)...], permv, share, h))
+        h[]
+    end
+end
+
+method_code(::PointToPoint) = Cint(0)
+method_code(::Alltoallv) = Cint(1)
+
+function plan_handle(t::Transposition{T}) where {T}
+    H = handles(t.Pi.topology)
+    ex = Int64[extra_dims(t.Ai)...]
+    key = (objectid(t.Pi), objectid(t.Po), Tuple(ex), sizeof(T), method_code(t.method))
+    plan = get!(H.plans, key) do
+        h = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_plan_create, libpa), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Cint, Ptr{Ptr{Cvoid}}),
+            pencil_handle(H, t.Pi), pencil_handle(H, t.Po), length(ex), ex, sizeof(T),
+            method_code(t.method), h))
+        h[]
+    end
+    plan, H
+end
+
+const DeviceTransposition{T,N} = Transposition{T,N,<:Pencil,<:Pencil,
+    <:PencilArray{T,N,<:CuArray},<:PencilArray{T,N,<:CuArray}}
+
+# transpose!(t; waitall) (Transpositions.jl:170-179)
+function Transpositions.transpose!(t::DeviceTransposition; waitall = true)
+    plan, H = plan_handle(t)
+    flags = waitall ? Cuint(1) : Cuint(0)        # PA_WAITALL
+    check(ccall((:pa_transpose, libpa), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Ptr{Cvoid}),
+        plan, H.comm, devptr(parent(t.Ai)), devptr(parent(t.Ao)), flags, stream_ptr()))
+    t
+end
+
+# MPI.Waitall(t) (Transpositions.jl:127-130)
+function MPI.Waitall(t::DeviceTransposition)
+    plan, _ = plan_handle(t)
+    check(ccall((:pa_wait, libpa), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), plan, stream_ptr()))
+    nothing
+end
+
+end # module
