@@ -226,7 +226,8 @@ def run_b200(args):
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
     ux.data.view(torch.float64).normal_(generator=gen)
     orig = ux.data.clone()
-    method = pa.Alltoallv() if args.method == "alltoallv" else pa.PointToPoint()
+    method = {"alltoallv": pa.Alltoallv(), "pointtopoint": pa.PointToPoint(),
+              "peerput": pa.PeerPut()}[args.method]
     ts = [pa.Transposition(uy, ux, method=method), pa.Transposition(uz, uy, method=method),
           pa.Transposition(uy, uz, method=method), pa.Transposition(ux, uy, method=method)]
     overlap = not args.no_overlap
@@ -448,7 +449,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--method", default="pointtopoint", choices=["pointtopoint", "alltoallv"])
+    ap.add_argument("--method", default="pointtopoint",
+                    choices=["pointtopoint", "alltoallv", "peerput"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -51,7 +51,13 @@ typedef enum pa_status {
 
 typedef enum pa_method {
   PA_POINT_TO_POINT = 0, /* Transpositions.PointToPoint  (Transpositions.jl:18) */
-  PA_ALLTOALLV = 1       /* Transpositions.Alltoallv     (Transpositions.jl:19) */
+  PA_ALLTOALLV = 1,      /* Transpositions.Alltoallv     (Transpositions.jl:19) */
+  PA_PEER_PUT = 2        /* B200 extension (no reference counterpart): one-sided puts.
+                            The pack kernel of each remote block stores straight into
+                            the destination rank's `dest` array over NVLink (peer-mapped
+                            memory): no send_buf, no recv_buf, no unpack pass.  Needs
+                            pa_plan_set_window for `dest`; falls back to PointToPoint
+                            when src and dest alias.                                   */
 } pa_method;
 
 /* flags of pa_transpose */
@@ -159,7 +165,8 @@ pa_status pa_plan_get_peer(const pa_plan* plan, int n /*1-based*/, pa_peer_info*
 /* Strided-copy descriptor of one block as the kernels see it, exported so
  * tests can compare the C++ plan with the oracle's independent derivation.
  * op: 0 = pack (src parent -> contiguous), 1 = unpack (contiguous -> dest
- * parent), 2 = fused self/local (src parent -> dest parent).
+ * parent), 2 = fused self/local (src parent -> dest parent), 3 = put (src
+ * parent -> peer n's dest parent, in the peer's layout; self: empty).
  * Dims are listed in the source's memory order incl. merged extra dims;
  * strides and offsets in elements.                                           */
 typedef struct pa_block_desc {
@@ -185,6 +192,11 @@ pa_status pa_unpack(pa_plan* plan, int n, const void* recv_buf, void* dst, void*
 /* K3 fused self block: src parent -> permuted dest parent in one pass
  * (replaces :393-403 followed by :527-529 for the local block)              */
 pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream);
+/* K1-put: block for peer n read from `src` and stored, already permuted, into
+ * `peer_dst` = peer n's dest parent array (any pointer this device can write:
+ * an IPC/peer mapping, a symmetric heap, or -- for tests -- local memory).
+ * Replaces :406-412 + the peer's :527-529 for that block in one pass.         */
+pa_status pa_put(pa_plan* plan, int n, const void* src, void* peer_dst, void* stream);
 /* transpose_impl!(::Nothing) / permute_local! (:213-270).  `scratch` must hold
  * length_out elements when src and dst alias, may be NULL otherwise.        */
 pa_status pa_permute_local(pa_plan* plan, const void* src, void* dst,
@@ -202,6 +214,20 @@ pa_status pa_box_copy(int nd, const int64_t* extent, const int64_t* src_stride,
 pa_status pa_comm_unique_id(void* id128);
 pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** out);
 void pa_comm_destroy(pa_comm* c);
+
+/* ---- PeerPut windows (PA_PEER_PUT) -----------------------------------------
+ * The analogue of a collective MPI_Win_create over `dest`: every rank exports
+ * an IPC handle of its `dest` array, hands it to the peers of its grid line by
+ * any side channel (the host mirror uses the same channel as the NCCL id), and
+ * registers the mapped peer pointers with the plan.                          */
+#define PA_IPC_HANDLE_BYTES 64
+/* handle of the device allocation containing `devptr` + byte offset of devptr in it */
+pa_status pa_ipc_export(const void* devptr, void* handle64, int64_t* offset);
+/* map a peer's allocation (cached per handle) and return base + offset */
+pa_status pa_ipc_import(const void* handle64, int64_t offset, void** mapped);
+/* `peer_dst` = peer n's (1-based index in the grid line) dest array as mapped here;
+ * `local_dst` = this rank's dest array the window belongs to                   */
+pa_status pa_plan_set_window(pa_plan* plan, const void* local_dst, int n, void* peer_dst);
 
 /* ---- transpose! ----------------------------------------------------------
  * transpose!(t; waitall) (Transpositions.jl:170-179) for device arrays.

@@ -18,6 +18,8 @@ PA_OK, PA_EINVAL, PA_EINCOMPAT, PA_EDIM, PA_ECUDA, PA_ENCCL, PA_ENOMEM, PA_ESTAT
 
 PA_POINT_TO_POINT = 0
 PA_ALLTOALLV = 1
+PA_PEER_PUT = 2
+PA_IPC_HANDLE_BYTES = 64
 
 PA_WAITALL = 1
 PA_NO_OVERLAP = 2
@@ -90,6 +92,7 @@ SIGNATURES = {
     "pa_plan_get_block": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(BlockDesc)]),
     "pa_pack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_unpack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pa_put": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_copy_self": (C.c_int, [_P, _P, _P, _P]),
     "pa_permute_local": (C.c_int, [_P, _P, _P, _P, _P]),
     "pa_box_copy": (C.c_int, [C.c_int, _I64P, _I64P, _I64P, C.c_int, _P, _P, _P,
@@ -97,6 +100,9 @@ SIGNATURES = {
     "pa_comm_unique_id": (C.c_int, [_P]),
     "pa_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "pa_comm_destroy": (None, [_P]),
+    "pa_ipc_export": (C.c_int, [_P, _P, _I64P]),
+    "pa_ipc_import": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
+    "pa_plan_set_window": (C.c_int, [_P, _P, C.c_int, _P]),
     "pa_transpose": (C.c_int, [_P, _P, _P, _P, C.c_uint, _P]),
     "pa_wait": (C.c_int, [_P, _P]),
     "pa_transpose_host": (C.c_int, [_P, _P, _P, _P, C.c_uint]),

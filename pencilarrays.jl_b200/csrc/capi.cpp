@@ -340,11 +340,12 @@ pa_status pa_plan_get_block(const pa_plan* plan, int op, int n, pa_block_desc* d
     export_block(P.self_fused, desc);
     return PA_OK;
   }
-  if (P.dim < 0 || n < 1 || n > P.nproc || (op != 0 && op != 1)) {
+  if (P.dim < 0 || n < 1 || n > P.nproc || (op != 0 && op != 1 && op != 3)) {
     set_error("bad block selector (op=%d, n=%d)", op, n);
     return PA_EINVAL;
   }
-  export_block(op == 0 ? P.peers[n - 1].pack : P.peers[n - 1].unpack, desc);
+  const Peer& pr = P.peers[n - 1];
+  export_block(op == 0 ? pr.pack : op == 1 ? pr.unpack : pr.put, desc);
   return PA_OK;
 }
 
@@ -379,6 +380,18 @@ pa_status pa_unpack(pa_plan* plan, int n, const void* recv_buf, void* dst, void*
   pa_status s = need_gpu();
   if (s != PA_OK) return s;
   return launch_block(P.peers[n - 1].unpack, recv_buf, dst, stream, nullptr);
+}
+
+pa_status pa_put(pa_plan* plan, int n, const void* src, void* peer_dst, void* stream) {
+  if (!plan) return PA_EINVAL;
+  Plan& P = *plan->p;
+  if (P.dim < 0 || n < 1 || n > P.nproc || P.peers[n - 1].is_self) {
+    set_error("pa_put: peer index %d out of range (or self)", n);
+    return PA_EINVAL;
+  }
+  pa_status s = need_gpu();
+  if (s != PA_OK) return s;
+  return launch_block(P.peers[n - 1].put, src, peer_dst, stream, nullptr);
 }
 
 pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream) {
@@ -451,6 +464,26 @@ void pa_comm_destroy(pa_comm* c) {
   if (!c) return;
   comm_destroy(c->p);
   delete c;
+}
+
+// ---- PeerPut windows ---------------------------------------------------------------
+pa_status pa_ipc_export(const void* devptr, void* handle64, int64_t* offset) {
+  if (!devptr || !handle64 || !offset) return PA_EINVAL;
+  return ipc_export(devptr, handle64, offset);
+}
+
+pa_status pa_ipc_import(const void* handle64, int64_t offset, void** mapped) {
+  GUARD({
+    if (!handle64 || !mapped) return PA_EINVAL;
+    return ipc_import(handle64, offset, mapped);
+  })
+}
+
+pa_status pa_plan_set_window(pa_plan* plan, const void* local_dst, int n, void* peer_dst) {
+  GUARD({
+    if (!plan || !local_dst) return PA_EINVAL;
+    return plan_set_window(plan->p, local_dst, n - 1, peer_dst);
+  })
 }
 
 // ---- transpose! ------------------------------------------------------------------

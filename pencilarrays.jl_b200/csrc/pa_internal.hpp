@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -109,6 +110,7 @@ struct Peer {
   i64 recv_off = 0, recv_cnt = 0;  // elements
   BlockCopy pack;    // K1: src parent box -> contiguous @ (send_off | recv_off)
   BlockCopy unpack;  // K2: contiguous @ recv_off -> dest parent box
+  BlockCopy put;     // K1-put: src parent box -> the PEER's dest parent (its layout), no staging
 };
 
 struct TransposeState;  // streams/events, defined in transpose.cpp
@@ -129,6 +131,9 @@ struct Plan {
   std::vector<Peer> peers;
   BlockCopy self_fused;  // K3: src parent -> dest parent (self block or local permute)
   TransposeState* st = nullptr;
+  // PeerPut windows: local dest base pointer -> peer-mapped dest base pointers
+  // (indexed by position in the grid line; nullptr for self)
+  std::map<const void*, std::vector<void*>> windows;
   // host-transpose staging
   void* h_src_dev = nullptr;
   void* h_dst_dev = nullptr;
@@ -152,6 +157,11 @@ pa_status transpose_host(Plan* plan, Comm* comm, const void* hsrc, void* hdst, u
 pa_status plan_timings(Plan* plan, pa_timings* t);
 pa_status plan_enable_timing(Plan* plan, int on);
 void destroy_state(TransposeState* st);
+
+// CUDA IPC plumbing of the PeerPut method (one-sided puts over NVLink)
+pa_status ipc_export(const void* devptr, void* handle64, i64* offset);
+pa_status ipc_import(const void* handle64, i64 offset, void** mapped);
+pa_status plan_set_window(Plan* plan, const void* local_dst, int n0, void* peer_dst);
 
 int device_count();
 pa_status set_device(int dev);

@@ -149,9 +149,9 @@ struct LocalLayout {
 
 // parent(A) has dims (perm * size_local) in memory order (Pencils.jl:229;
 // arrays.jl:108-114): memory dim m holds logical dim perm[m].
-LocalLayout layout_of(const Pencil& p) {
+LocalLayout layout_of(const Pencil& p, const i64* coords = nullptr) {
   LocalLayout L;
-  p.range_local(L.lo, L.hi);
+  p.range_of(coords ? coords : p.topo->coords, L.lo, L.hi);
   L.total = 1;
   for (int d = 0; d < p.N; ++d) L.len[d] = L.hi[d] - L.lo[d];
   i64 run = 1;
@@ -203,7 +203,7 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
     set_error("invalid element size %d", elsize);
     return PA_EINVAL;
   }
-  if (method != PA_POINT_TO_POINT && method != PA_ALLTOALLV) {
+  if (method != PA_POINT_TO_POINT && method != PA_ALLTOALLV && method != PA_PEER_PUT) {
     set_error("unknown transposition method %d", method);
     return PA_EINVAL;
   }
@@ -245,6 +245,7 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
   // helper: append one block's dims in SOURCE memory order.
   // `src_contig` / `dst_contig`: that side is a dense buffer whose dims are the
   // box extents in Pi memory order (wire layout, Transpositions.jl:552-565).
+  const LocalLayout* Ldst = &Lo;  // destination parent layout used by make_block (a peer's for K1-put)
   auto make_block = [&](const i64* blo, const i64* bhi, bool src_contig, bool dst_contig,
                         i64 src_base, i64 dst_base) {
     BlockCopy b;
@@ -257,13 +258,13 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
       int l = Pi.perm[m];
       i64 e = std::max<i64>(0, bhi[l] - blo[l]);
       i64 ss = src_contig ? run : Li.stride[l] * sub;
-      i64 ds = dst_contig ? run : Lo.stride[l] * sub;
+      i64 ds = dst_contig ? run : Ldst->stride[l] * sub;
       if (!src_contig) soff += (blo[l] - Li.lo[l]) * Li.stride[l] * sub;
-      if (!dst_contig) doff += (blo[l] - Lo.lo[l]) * Lo.stride[l] * sub;
+      if (!dst_contig) doff += (blo[l] - Ldst->lo[l]) * Ldst->stride[l] * sub;
       b.raw[k++] = Dim{e, ss, ds};
       run *= e;
     }
-    i64 es = Li.total * sub, ed = Lo.total * sub;  // strides of the first extra dim in a parent
+    i64 es = Li.total * sub, ed = Ldst->total * sub;  // strides of the first extra dim in a parent
     for (int j = 0; j < n_extra; ++j) {
       i64 e = P->extra[j];
       b.raw[k++] = Dim{e, src_contig ? run : es, dst_contig ? run : ed};
@@ -346,7 +347,16 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
       irecv += rc;
     }
     pr.unpack = make_block(rlo, rhi, true, false, pr.recv_off, 0);
-    if (pr.is_self) P->self_fused = make_block(slo, shi, false, false, 0, 0);
+    if (pr.is_self) {
+      P->self_fused = make_block(slo, shi, false, false, 0, 0);
+    } else {
+      // K1-put: my send box written straight into peer n's dest parent, which has
+      // the PEER's local layout (uneven blocks: its extents differ from mine)
+      const LocalLayout Lpeer = layout_of(Po, coords);
+      Ldst = &Lpeer;
+      pr.put = make_block(slo, shi, false, false, 0, 0);
+      Ldst = &Lo;
+    }
   }
   if (isend != P->send_elems || irecv != length_recv) {
     set_error("internal error: block sizes do not tile the local arrays (%lld/%lld, %lld/%lld)",

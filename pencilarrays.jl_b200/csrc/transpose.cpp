@@ -41,6 +41,72 @@ pa_status set_device(int dev) {
   return PA_OK;
 }
 
+// ---- CUDA IPC: windows of the PeerPut method -----------------------------------
+typedef int (*cuMemGetAddressRange_fn)(unsigned long long*, size_t*, unsigned long long);
+
+static cuMemGetAddressRange_fn addr_range_fn() {
+  static cuMemGetAddressRange_fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return (cuMemGetAddressRange_fn)f;
+  }();
+  return fn;
+}
+
+pa_status ipc_export(const void* devptr, void* handle64, i64* offset) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == PA_IPC_HANDLE_BYTES, "ipc handle size");
+  if (device_count() == 0) {
+    set_error("no CUDA device");
+    return PA_ENOGPU;
+  }
+  CU(cudaFree(nullptr));  // make sure this runtime instance has its context
+  cuMemGetAddressRange_fn fn = addr_range_fn();
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (!fn || fn(&base, &size, (unsigned long long)(uintptr_t)devptr) != 0) {
+    set_error("cuMemGetAddressRange failed for %p (not a device allocation?)", devptr);
+    return PA_ECUDA;
+  }
+  cudaIpcMemHandle_t h;
+  CU(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+  memcpy(handle64, &h, sizeof h);
+  *offset = (i64)((unsigned long long)(uintptr_t)devptr - base);
+  return PA_OK;
+}
+
+pa_status ipc_import(const void* handle64, i64 offset, void** mapped) {
+  static std::mutex mu;
+  static std::map<std::string, void*> cache;  // one mapping per peer allocation, kept for the process
+  std::lock_guard<std::mutex> lock(mu);
+  std::string key((const char*)handle64, PA_IPC_HANDLE_BYTES);
+  auto it = cache.find(key);
+  void* base = nullptr;
+  if (it != cache.end()) {
+    base = it->second;
+  } else {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    cache[key] = base;
+  }
+  *mapped = (char*)base + offset;
+  return PA_OK;
+}
+
+pa_status plan_set_window(Plan* P, const void* local_dst, int n0, void* peer_dst) {
+  if (P->dim < 0 || n0 < 0 || n0 >= P->nproc) {
+    set_error("window peer index out of range");
+    return PA_EINVAL;
+  }
+  std::vector<void*>& v = P->windows[local_dst];
+  v.resize(P->nproc, nullptr);
+  v[n0] = peer_dst;
+  return PA_OK;
+}
+
 // ---- NCCL via dlopen ---------------------------------------------------------
 struct NcclApi {
   void* h = nullptr;
@@ -172,6 +238,7 @@ struct TransposeState {
   bool timed_once = false;
   cudaEvent_t t[8] = {nullptr};  // 0 start,1 pack_end,2 comm0,3 comm1,4 unpack0,5 unpack1,6 end
   bool sends_pending = false;
+  char* tok = nullptr;  // 4-byte tokens of the PeerPut line barrier: [0] sent, [1+n] received from n
 };
 
 void destroy_state(TransposeState* st) {
@@ -186,6 +253,7 @@ void destroy_state(TransposeState* st) {
   for (auto e : st->ev_recvd) cudaEventDestroy(e);
   for (auto e : st->t)
     if (e) cudaEventDestroy(e);
+  if (st->tok) cudaFree(st->tok);
   delete st;
 }
 
@@ -217,6 +285,8 @@ static pa_status ensure_state(Plan* P) {
     CU(cudaEventCreateWithFlags(&st->ev_recvd[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < 7; ++i) CU(cudaEventCreate(&st->t[i]));
+  CU(cudaMalloc((void**)&st->tok, 4 * (size_t)(P->nproc + 1)));
+  CU(cudaMemset(st->tok, 0, 4 * (size_t)(P->nproc + 1)));
   P->st = st.release();
   return PA_OK;
 }
@@ -321,7 +391,7 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   const bool aliased = ranges_overlap(src, P->length_in * ES, dst, P->length_out * ES);
   const bool stage_self = aliased || (flags & PA_STAGE_SELF);
   const bool overlap = !(flags & PA_NO_OVERLAP);
-  {
+  if (!(P->method == PA_PEER_PUT && !stage_self && nproc > 1)) {  // puts need no staging arenas
     i64 need_send = nproc > 1 ? std::max<i64>(1, P->send_elems * ES) : 0;
     i64 need_recv = (nproc > 1 || stage_self) ? std::max<i64>(1, P->recv_elems * ES) : 0;
     rc = B.reserve(need_send, need_recv);
@@ -374,6 +444,67 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
     return PA_OK;
   };
 
+  // ---- PeerPut: one-sided puts over NVLink, no staging ------------------------
+  // Each remote block is read from `src` and stored, already permuted, into the
+  // destination rank's `dest` through its peer mapping; two tiny grouped
+  // send/recv rounds among the line's ranks act as the window fences
+  // ("every dest may be overwritten" / "every put has landed").
+  if (P->method == PA_PEER_PUT && !stage_self) {
+    auto w = P->windows.find(dst);
+    if (w == P->windows.end()) {
+      set_error("PeerPut: `dest` has no registered window (pa_plan_set_window)");
+      return PA_ESTATE;
+    }
+    const std::vector<void*>& win = w->second;
+    for (int n = 0; n < nproc; ++n)
+      if (n != me && P->peers[n].send_cnt > 0 && !win[n]) {
+        set_error("PeerPut: window of peer %d is missing", n + 1);
+        return PA_ESTATE;
+      }
+    auto line_barrier = [&]() -> pa_status {
+      NC(nccl().GroupStart());
+      for (int k = 1; k < nproc; ++k) {
+        const int to = (me + k) % nproc, from = (me - k + nproc) % nproc;
+        NC(nccl().Send(S.tok, 4, ncclUint8, P->peers[to].world_rank, comm->comm, S.comm_s));
+        NC(nccl().Recv(S.tok + 4 * (1 + from), 4, ncclUint8, P->peers[from].world_rank, comm->comm,
+                       S.comm_s));
+      }
+      NC(nccl().GroupEnd());
+      return PA_OK;
+    };
+    if (timing) CU(cudaEventRecord(S.t[4], S.unpack_s));
+    rc = launch_block(P->self_fused, src, dst, S.unpack_s, nullptr);
+    if (rc != PA_OK) return rc;
+    CU(cudaEventRecord(S.ev_unpack_done, S.unpack_s));
+    if (timing) CU(cudaEventRecord(S.t[5], S.unpack_s));
+    if (timing) CU(cudaEventRecord(S.t[2], S.comm_s));
+    rc = line_barrier();
+    if (rc != PA_OK) return rc;
+    CU(cudaEventRecord(S.ev_recvd[0], S.comm_s));
+    CU(cudaStreamWaitEvent(S.pack_s, S.ev_recvd[0], 0));
+    for (int k = 1; k < nproc; ++k) {
+      const int to = (me + k) % nproc;
+      rc = launch_block(P->peers[to].put, src, win[to], S.pack_s, nullptr);
+      if (rc != PA_OK) return rc;
+    }
+    CU(cudaEventRecord(S.ev_allpacked, S.pack_s));
+    if (timing) CU(cudaEventRecord(S.t[1], S.pack_s));
+    CU(cudaStreamWaitEvent(S.comm_s, S.ev_allpacked, 0));
+    rc = line_barrier();
+    if (rc != PA_OK) return rc;
+    CU(cudaEventRecord(S.ev_comm_done, S.comm_s));
+    if (timing) CU(cudaEventRecord(S.t[3], S.comm_s));
+    CU(cudaStreamWaitEvent(user, S.ev_allpacked, 0));
+    CU(cudaStreamWaitEvent(user, S.ev_unpack_done, 0));
+    CU(cudaStreamWaitEvent(user, S.ev_comm_done, 0));  // dest complete only after the closing fence
+    S.sends_pending = false;
+    if (timing) {
+      CU(cudaEventRecord(S.t[6], user));
+      S.timed_once = true;
+    }
+    return PA_OK;
+  }
+
   // ---- 1. pack (+ exchange) -------------------------------------------------
   if (stage_self) {
     rc = launch_block(self.pack, src, rbuf, S.pack_s, nullptr);  // tail of recv_buf (:393-403)
@@ -382,7 +513,7 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   }
   if (rc != PA_OK) return rc;
 
-  const bool p2p = P->method == PA_POINT_TO_POINT;
+  const bool p2p = P->method != PA_ALLTOALLV;  // PeerPut with aliased arrays runs staged, as PointToPoint
   for (int k = 1; k < nproc; ++k) {
     const int to = (me + k) % nproc;
     rc = launch_block(P->peers[to].pack, src, sbuf, S.pack_s, nullptr);

@@ -45,6 +45,19 @@ class Alltoallv(AbstractTransposeMethod):  # Transpositions.jl:19
     code = _lib.PA_ALLTOALLV
 
 
+class PeerPut(AbstractTransposeMethod):
+    """B200 extension (no reference counterpart): one-sided puts over NVLink.
+
+    Each remote block is packed by a kernel that stores straight into the
+    destination rank's ``dest`` array through a peer mapping -- no ``send_buf``,
+    no ``recv_buf``, no unpack pass.  ``Transposition(dest, src; method=PeerPut())``
+    is COLLECTIVE over the communicator (like ``MPI_Win_create``): it exchanges
+    CUDA IPC handles of ``dest``.  Falls back to the staged PointToPoint
+    schedule when ``src`` and ``dest`` alias (in-place transposes).
+    """
+    code = _lib.PA_PEER_PUT
+
+
 class _Plan:
     """Owner of one ``pa_plan`` handle (geometry + launch descriptors + streams)."""
 
@@ -99,6 +112,41 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
+    """Collective: expose ``Ao``'s device buffer to the peers of the grid line and
+    map theirs (``pa_ipc_export`` / ``pa_ipc_import`` / ``pa_plan_set_window``).
+    Cached per destination array; SPMD programs hit or miss the cache together."""
+    import weakref
+    import torch.distributed as dist
+
+    lo, hi = Ao.data_ptr(), Ao.data_ptr() + Ao.data.numel() * Ao.elsize
+    si, ei = Ai.data_ptr(), Ai.data_ptr() + Ai.data.numel() * Ai.elsize
+    if lo < ei and si < hi:
+        return  # aliased (in-place): libpa_b200 takes the staged schedule, no window needed
+    reg = plan.__dict__.setdefault("_windows", {})
+    ent = reg.get(id(Ao))
+    if ent is not None and ent[0]() is Ao and ent[1] == lo:
+        return
+    if not dist.is_initialized():
+        raise ArgumentError(_lib.PA_EINVAL, "PeerPut needs torch.distributed for the handle exchange")
+    _stream_ptr()  # binds the library to torch's current device
+    h = C.create_string_buffer(_lib.PA_IPC_HANDLE_BYTES)
+    off = C.c_int64()
+    check(lib.pa_ipc_export(C.c_void_p(lo), h, C.byref(off)))
+    allh = [None] * comm.size
+    dist.all_gather_object(allh, (comm.rank, bytes(h.raw), off.value))
+    byrank = {r: (hh, oo) for (r, hh, oo) in allh}
+    for n in range(1, plan.info.nproc + 1):
+        peer = plan.peer(n)
+        if peer.is_self:
+            continue
+        hh, oo = byrank[peer.world_rank]
+        mapped = C.c_void_p()
+        check(lib.pa_ipc_import(hh, oo, C.byref(mapped)))
+        check(lib.pa_plan_set_window(plan.h, C.c_void_p(lo), n, mapped))
+    reg[id(Ao)] = (weakref.ref(Ao), lo)
+
+
 class Transposition:
     """Holds data for transposition between two pencil configurations (:69-119)."""
 
@@ -118,6 +166,8 @@ class Transposition:
         self._plan = _get_plan(Pi, Po, Ai.extra_dims, Ai.elsize, method)  # remaining checks in C
         d = self._plan.info.dim
         self.dim = None if d == 0 else d  # :110
+        if isinstance(method, PeerPut) and d != 0 and self._plan.info.nproc > 1:
+            _register_window(self._plan, Ao, Ai, Pi.topology.comm)
 
     @property
     def plan(self) -> _Plan:

@@ -87,7 +87,8 @@ def main():
         g = O.global_pattern(case["dims"], extra, it)
         cur_o = O.scatter(g, opens[0], extra, dtype)
         variants = [(pa.PointToPoint(), True, True), (pa.PointToPoint(), False, True),
-                    (pa.Alltoallv(), True, True), (pa.PointToPoint(), True, False)]
+                    (pa.Alltoallv(), True, True), (pa.PointToPoint(), True, False),
+                    (pa.PeerPut(), True, True)]
         if mode == "gloo":
             cur = cur_o[rank].data.reshape(-1, order="F").copy()
         else:

@@ -62,6 +62,38 @@ def test_reference_cases_emulated_ranks(case, fused_self):
         cur = [t[:max(1, o.data.size * it)] for t, o in zip(nxt, nxt_o)]
 
 
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_put_kernels_emulated_ranks(case):
+    """K1-put (`pa_put`): each block stored directly into the destination rank's
+    parent array -- here the emulated peers' arrays on the same GPU."""
+    dtype, it, extra = DTYPES[case["it"]], case["it"], case["extra"]
+    ranks, steps = build_chain(case)
+    g = O.global_pattern(case["dims"], extra, it)
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], extra, dtype)
+    from gpu_util import stream_ptr
+    for k in range(1, len(steps)):
+        nxt_o = [O.OArray.undef(dtype, po, *extra) for (_, po) in steps[k]]
+        O.transpose_all(nxt_o, cur_o)
+        plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], extra, it, pa.PeerPut())
+                 for r in range(len(ranks))]
+        if plans[0].info.dim != 0:
+            cur = [dev_bytes(a.data.reshape(-1, order="F")) for a in cur_o]
+            nxt = [torch.full((max(1, a.data.size * it),), 0xA5, dtype=torch.uint8, device="cuda")
+                   for a in nxt_o]
+            st = stream_ptr()
+            for r, pl in enumerate(plans):
+                check(lib.pa_copy_self(pl.h, ptr(cur[r]), ptr(nxt[r]), st))
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if not peer.is_self:
+                        check(lib.pa_put(pl.h, p, ptr(cur[r]), ptr(nxt[peer.world_rank]), st))
+            torch.cuda.synchronize()
+            for r, a in enumerate(nxt_o):
+                want = np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8)
+                assert host_bytes(nxt[r])[:want.size].tobytes() == want.tobytes(), (k, r)
+        cur_o = nxt_o
+
+
 # ---------------------------------------------------------------- public API, one rank
 def _fill(u: pa.PencilArray, seed):
     raw = torch.randint(0, 256, (u.data.numel() * u.elsize,), dtype=torch.uint8, device="cuda",

@@ -70,6 +70,35 @@ def test_fused_self_block_equals_pack_then_unpack():
         assert beq(a, b)
 
 
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_put_descriptors_match_oracle(case):
+    """PeerPut: every block written straight into the DESTINATION rank's parent
+    array (descriptor op 3, in the peer's layout) + the fused self block must
+    reproduce the oracle's result without any staging buffer."""
+    from util import apply_block
+    dtype, extra = DTYPES[case["it"]], case["extra"]
+    ranks, steps = build_chain(case)
+    g = O.global_pattern(case["dims"], extra, case["it"])
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], extra, dtype)
+    for k in range(1, len(steps)):
+        nxt_o = [O.OArray.undef(dtype, po, *extra) for (_, po) in steps[k]]
+        O.transpose_all(nxt_o, cur_o)
+        plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], extra, case["it"], pa.PeerPut())
+                 for r in range(len(ranks))]
+        if plans[0].info.dim != 0:
+            cur = [a.data.reshape(-1, order="F") for a in cur_o]
+            nxt = [np.zeros(max(1, a.data.size), dtype=dtype) for a in nxt_o]
+            for r, pl in enumerate(plans):
+                apply_block(pl.block(2), cur[r], nxt[r])
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if not peer.is_self:
+                        apply_block(pl.block(3, p), cur[r], nxt[peer.world_rank])
+            for r, a in enumerate(nxt_o):
+                assert beq(nxt[r][:a.data.size], a.data.reshape(-1, order="F")), (k, r)
+        cur_o = nxt_o
+
+
 def test_counts_are_symmetric():
     """send count r->q equals recv count q<-r for every pair (what Isend/Irecv rely on)."""
     for case in CASES:
