@@ -227,7 +227,7 @@ def run_b200(args):
     ux.data.view(torch.float64).normal_(generator=gen)
     orig = ux.data.clone()
     method = {"alltoallv": pa.Alltoallv(), "pointtopoint": pa.PointToPoint(),
-              "peerput": pa.PeerPut()}[args.method]
+              "peerput": pa.PeerPut(), "peerget": pa.PeerGet()}[args.method]
     ts = [pa.Transposition(uy, ux, method=method), pa.Transposition(uz, uy, method=method),
           pa.Transposition(uy, uz, method=method), pa.Transposition(ux, uy, method=method)]
     overlap = not args.no_overlap
@@ -450,7 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="pointtopoint",
-                    choices=["pointtopoint", "alltoallv", "peerput"])
+                    choices=["pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

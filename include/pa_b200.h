@@ -58,6 +58,10 @@ typedef enum pa_method {
                             memory): no send_buf, no recv_buf, no unpack pass.  Needs
                             pa_plan_set_window for `dest`; falls back to PointToPoint
                             when src and dest alias.                                   */
+  PA_PEER_GET = 3        /* same, pull flavour: the unpack kernel of each remote block
+                            LOADS straight out of the source rank's `src` array over
+                            NVLink and stores permuted into the local `dest`.  Needs
+                            pa_plan_set_window for `src`.                              */
 } pa_method;
 
 /* flags of pa_transpose */
@@ -166,7 +170,8 @@ pa_status pa_plan_get_peer(const pa_plan* plan, int n /*1-based*/, pa_peer_info*
  * tests can compare the C++ plan with the oracle's independent derivation.
  * op: 0 = pack (src parent -> contiguous), 1 = unpack (contiguous -> dest
  * parent), 2 = fused self/local (src parent -> dest parent), 3 = put (src
- * parent -> peer n's dest parent, in the peer's layout; self: empty).
+ * parent -> peer n's dest parent, in the peer's layout; self: empty), 4 = get
+ * (peer n's src parent, in its layout -> dest parent).
  * Dims are listed in the source's memory order incl. merged extra dims;
  * strides and offsets in elements.                                           */
 typedef struct pa_block_desc {
@@ -197,6 +202,9 @@ pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream);
  * an IPC/peer mapping, a symmetric heap, or -- for tests -- local memory).
  * Replaces :406-412 + the peer's :527-529 for that block in one pass.         */
 pa_status pa_put(pa_plan* plan, int n, const void* src, void* peer_dst, void* stream);
+/* K2-get: the block peer n holds for this rank, loaded from `peer_src` = peer
+ * n's src parent array (its layout) and stored permuted into `dst`.           */
+pa_status pa_get(pa_plan* plan, int n, const void* peer_src, void* dst, void* stream);
 /* transpose_impl!(::Nothing) / permute_local! (:213-270).  `scratch` must hold
  * length_out elements when src and dst alias, may be NULL otherwise.        */
 pa_status pa_permute_local(pa_plan* plan, const void* src, void* dst,

@@ -19,6 +19,7 @@ PA_OK, PA_EINVAL, PA_EINCOMPAT, PA_EDIM, PA_ECUDA, PA_ENCCL, PA_ENOMEM, PA_ESTAT
 PA_POINT_TO_POINT = 0
 PA_ALLTOALLV = 1
 PA_PEER_PUT = 2
+PA_PEER_GET = 3
 PA_IPC_HANDLE_BYTES = 64
 
 PA_WAITALL = 1
@@ -93,6 +94,7 @@ SIGNATURES = {
     "pa_pack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_unpack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_put": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pa_get": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_copy_self": (C.c_int, [_P, _P, _P, _P]),
     "pa_permute_local": (C.c_int, [_P, _P, _P, _P, _P]),
     "pa_box_copy": (C.c_int, [C.c_int, _I64P, _I64P, _I64P, C.c_int, _P, _P, _P,

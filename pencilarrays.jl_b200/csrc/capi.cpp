@@ -340,12 +340,12 @@ pa_status pa_plan_get_block(const pa_plan* plan, int op, int n, pa_block_desc* d
     export_block(P.self_fused, desc);
     return PA_OK;
   }
-  if (P.dim < 0 || n < 1 || n > P.nproc || (op != 0 && op != 1 && op != 3)) {
+  if (P.dim < 0 || n < 1 || n > P.nproc || op < 0 || op > 4) {
     set_error("bad block selector (op=%d, n=%d)", op, n);
     return PA_EINVAL;
   }
   const Peer& pr = P.peers[n - 1];
-  export_block(op == 0 ? pr.pack : op == 1 ? pr.unpack : pr.put, desc);
+  export_block(op == 0 ? pr.pack : op == 1 ? pr.unpack : op == 3 ? pr.put : pr.get, desc);
   return PA_OK;
 }
 
@@ -392,6 +392,18 @@ pa_status pa_put(pa_plan* plan, int n, const void* src, void* peer_dst, void* st
   pa_status s = need_gpu();
   if (s != PA_OK) return s;
   return launch_block(P.peers[n - 1].put, src, peer_dst, stream, nullptr);
+}
+
+pa_status pa_get(pa_plan* plan, int n, const void* peer_src, void* dst, void* stream) {
+  if (!plan) return PA_EINVAL;
+  Plan& P = *plan->p;
+  if (P.dim < 0 || n < 1 || n > P.nproc || P.peers[n - 1].is_self) {
+    set_error("pa_get: peer index %d out of range (or self)", n);
+    return PA_EINVAL;
+  }
+  pa_status s = need_gpu();
+  if (s != PA_OK) return s;
+  return launch_block(P.peers[n - 1].get, peer_src, dst, stream, nullptr);
 }
 
 pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream) {

@@ -111,6 +111,7 @@ struct Peer {
   BlockCopy pack;    // K1: src parent box -> contiguous @ (send_off | recv_off)
   BlockCopy unpack;  // K2: contiguous @ recv_off -> dest parent box
   BlockCopy put;     // K1-put: src parent box -> the PEER's dest parent (its layout), no staging
+  BlockCopy get;     // K2-get: the PEER's src parent box (its layout) -> dest parent box
 };
 
 struct TransposeState;  // streams/events, defined in transpose.cpp

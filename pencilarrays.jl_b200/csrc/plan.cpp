@@ -203,7 +203,7 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
     set_error("invalid element size %d", elsize);
     return PA_EINVAL;
   }
-  if (method != PA_POINT_TO_POINT && method != PA_ALLTOALLV && method != PA_PEER_PUT) {
+  if (method < PA_POINT_TO_POINT || method > PA_PEER_GET) {
     set_error("unknown transposition method %d", method);
     return PA_EINVAL;
   }
@@ -246,6 +246,7 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
   // `src_contig` / `dst_contig`: that side is a dense buffer whose dims are the
   // box extents in Pi memory order (wire layout, Transpositions.jl:552-565).
   const LocalLayout* Ldst = &Lo;  // destination parent layout used by make_block (a peer's for K1-put)
+  const LocalLayout* Lsrc = &Li;  // source parent layout (a peer's for K2-get)
   auto make_block = [&](const i64* blo, const i64* bhi, bool src_contig, bool dst_contig,
                         i64 src_base, i64 dst_base) {
     BlockCopy b;
@@ -257,14 +258,14 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
     for (int m = 0; m < N; ++m) {
       int l = Pi.perm[m];
       i64 e = std::max<i64>(0, bhi[l] - blo[l]);
-      i64 ss = src_contig ? run : Li.stride[l] * sub;
+      i64 ss = src_contig ? run : Lsrc->stride[l] * sub;
       i64 ds = dst_contig ? run : Ldst->stride[l] * sub;
-      if (!src_contig) soff += (blo[l] - Li.lo[l]) * Li.stride[l] * sub;
+      if (!src_contig) soff += (blo[l] - Lsrc->lo[l]) * Lsrc->stride[l] * sub;
       if (!dst_contig) doff += (blo[l] - Ldst->lo[l]) * Ldst->stride[l] * sub;
       b.raw[k++] = Dim{e, ss, ds};
       run *= e;
     }
-    i64 es = Li.total * sub, ed = Ldst->total * sub;  // strides of the first extra dim in a parent
+    i64 es = Lsrc->total * sub, ed = Ldst->total * sub;  // strides of the first extra dim in a parent
     for (int j = 0; j < n_extra; ++j) {
       i64 e = P->extra[j];
       b.raw[k++] = Dim{e, src_contig ? run : es, dst_contig ? run : ed};
@@ -356,6 +357,12 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
       Ldst = &Lpeer;
       pr.put = make_block(slo, shi, false, false, 0, 0);
       Ldst = &Lo;
+      // K2-get: the block peer n holds for me, read straight out of ITS src parent
+      // (its Pi layout) and stored permuted into my dest parent
+      const LocalLayout Lpin = layout_of(Pi, coords);
+      Lsrc = &Lpin;
+      pr.get = make_block(rlo, rhi, false, false, 0, 0);
+      Lsrc = &Li;
     }
   }
   if (isend != P->send_elems || irecv != length_recv) {

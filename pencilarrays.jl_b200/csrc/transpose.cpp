@@ -391,7 +391,8 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   const bool aliased = ranges_overlap(src, P->length_in * ES, dst, P->length_out * ES);
   const bool stage_self = aliased || (flags & PA_STAGE_SELF);
   const bool overlap = !(flags & PA_NO_OVERLAP);
-  if (!(P->method == PA_PEER_PUT && !stage_self && nproc > 1)) {  // puts need no staging arenas
+  if (!((P->method == PA_PEER_PUT || P->method == PA_PEER_GET) && !stage_self && nproc > 1)) {
+    // (one-sided puts/gets need no staging arenas)
     i64 need_send = nproc > 1 ? std::max<i64>(1, P->send_elems * ES) : 0;
     i64 need_recv = (nproc > 1 || stage_self) ? std::max<i64>(1, P->recv_elems * ES) : 0;
     rc = B.reserve(need_send, need_recv);
@@ -449,16 +450,20 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   // destination rank's `dest` through its peer mapping; two tiny grouped
   // send/recv rounds among the line's ranks act as the window fences
   // ("every dest may be overwritten" / "every put has landed").
-  if (P->method == PA_PEER_PUT && !stage_self) {
-    auto w = P->windows.find(dst);
+  // PeerGet is the pull flavour: the remote block is LOADED out of the source
+  // rank's `src` (window on src) and stored permuted into the local `dest`.
+  if ((P->method == PA_PEER_PUT || P->method == PA_PEER_GET) && !stage_self) {
+    const bool get = P->method == PA_PEER_GET;
+    auto w = P->windows.find(get ? src : (const void*)dst);
     if (w == P->windows.end()) {
-      set_error("PeerPut: `dest` has no registered window (pa_plan_set_window)");
+      set_error("one-sided transpose: `%s` has no registered window (pa_plan_set_window)",
+                get ? "src" : "dest");
       return PA_ESTATE;
     }
     const std::vector<void*>& win = w->second;
     for (int n = 0; n < nproc; ++n)
-      if (n != me && P->peers[n].send_cnt > 0 && !win[n]) {
-        set_error("PeerPut: window of peer %d is missing", n + 1);
+      if (n != me && (get ? P->peers[n].recv_cnt : P->peers[n].send_cnt) > 0 && !win[n]) {
+        set_error("one-sided transpose: window of peer %d is missing", n + 1);
         return PA_ESTATE;
       }
     auto line_barrier = [&]() -> pa_status {
@@ -483,8 +488,9 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
     CU(cudaEventRecord(S.ev_recvd[0], S.comm_s));
     CU(cudaStreamWaitEvent(S.pack_s, S.ev_recvd[0], 0));
     for (int k = 1; k < nproc; ++k) {
-      const int to = (me + k) % nproc;
-      rc = launch_block(P->peers[to].put, src, win[to], S.pack_s, nullptr);
+      const int to = (me + k) % nproc, from = (me - k + nproc) % nproc;
+      rc = get ? launch_block(P->peers[from].get, win[from], dst, S.pack_s, nullptr)
+               : launch_block(P->peers[to].put, src, win[to], S.pack_s, nullptr);
       if (rc != PA_OK) return rc;
     }
     CU(cudaEventRecord(S.ev_allpacked, S.pack_s));
@@ -496,8 +502,14 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
     if (timing) CU(cudaEventRecord(S.t[3], S.comm_s));
     CU(cudaStreamWaitEvent(user, S.ev_allpacked, 0));
     CU(cudaStreamWaitEvent(user, S.ev_unpack_done, 0));
-    CU(cudaStreamWaitEvent(user, S.ev_comm_done, 0));  // dest complete only after the closing fence
-    S.sends_pending = false;
+    // put: dest is complete only after the closing fence (peers' stores have landed);
+    // get: dest is complete once my loads are done, the closing fence only guards
+    //      the reuse of `src` -- exactly MPI.Waitall(t)'s role (:127-130).
+    S.sends_pending = true;
+    if (!get || (flags & PA_WAITALL)) {
+      CU(cudaStreamWaitEvent(user, S.ev_comm_done, 0));
+      S.sends_pending = false;
+    }
     if (timing) {
       CU(cudaEventRecord(S.t[6], user));
       S.timed_once = true;

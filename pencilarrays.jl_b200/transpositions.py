@@ -58,6 +58,14 @@ class PeerPut(AbstractTransposeMethod):
     code = _lib.PA_PEER_PUT
 
 
+class PeerGet(AbstractTransposeMethod):
+    """Pull flavour of :class:`PeerPut`: the unpack kernel of each remote block
+    loads straight out of the source rank's ``src`` array over NVLink.  The
+    window is on ``src``; ``waitall=False`` defers only the fence that guards
+    the reuse of ``src`` -- the role ``MPI.Waitall(t)`` has in the reference."""
+    code = _lib.PA_PEER_GET
+
+
 class _Plan:
     """Owner of one ``pa_plan`` handle (geometry + launch descriptors + streams)."""
 
@@ -166,8 +174,11 @@ class Transposition:
         self._plan = _get_plan(Pi, Po, Ai.extra_dims, Ai.elsize, method)  # remaining checks in C
         d = self._plan.info.dim
         self.dim = None if d == 0 else d  # :110
-        if isinstance(method, PeerPut) and d != 0 and self._plan.info.nproc > 1:
-            _register_window(self._plan, Ao, Ai, Pi.topology.comm)
+        if d != 0 and self._plan.info.nproc > 1:
+            if isinstance(method, PeerPut):
+                _register_window(self._plan, Ao, Ai, Pi.topology.comm)
+            elif isinstance(method, PeerGet):
+                _register_window(self._plan, Ai, Ao, Pi.topology.comm)
 
     @property
     def plan(self) -> _Plan:

@@ -88,7 +88,8 @@ def main():
         cur_o = O.scatter(g, opens[0], extra, dtype)
         variants = [(pa.PointToPoint(), True, True), (pa.PointToPoint(), False, True),
                     (pa.Alltoallv(), True, True), (pa.PointToPoint(), True, False),
-                    (pa.PeerPut(), True, True)]
+                    (pa.PeerPut(), True, True), (pa.PeerGet(), True, True),
+                    (pa.PeerGet(), True, False)]
         if mode == "gloo":
             cur = cur_o[rank].data.reshape(-1, order="F").copy()
         else:

@@ -91,6 +91,19 @@ def test_put_kernels_emulated_ranks(case):
             for r, a in enumerate(nxt_o):
                 want = np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8)
                 assert host_bytes(nxt[r])[:want.size].tobytes() == want.tobytes(), (k, r)
+            # K2-get (`pa_get`): pull each block out of the source rank's parent array
+            for t in nxt:
+                t.fill_(0x3C)
+            for r, pl in enumerate(plans):
+                check(lib.pa_copy_self(pl.h, ptr(cur[r]), ptr(nxt[r]), st))
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if not peer.is_self:
+                        check(lib.pa_get(pl.h, p, ptr(cur[peer.world_rank]), ptr(nxt[r]), st))
+            torch.cuda.synchronize()
+            for r, a in enumerate(nxt_o):
+                want = np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8)
+                assert host_bytes(nxt[r])[:want.size].tobytes() == want.tobytes(), ("get", k, r)
         cur_o = nxt_o
 
 

@@ -96,6 +96,16 @@ def test_put_descriptors_match_oracle(case):
                         apply_block(pl.block(3, p), cur[r], nxt[peer.world_rank])
             for r, a in enumerate(nxt_o):
                 assert beq(nxt[r][:a.data.size], a.data.reshape(-1, order="F")), (k, r)
+            # PeerGet: the same result pulled out of the SOURCE ranks' parents (op 4)
+            nxt = [np.zeros(max(1, a.data.size), dtype=dtype) for a in nxt_o]
+            for r, pl in enumerate(plans):
+                apply_block(pl.block(2), cur[r], nxt[r])
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if not peer.is_self:
+                        apply_block(pl.block(4, p), cur[peer.world_rank], nxt[r])
+            for r, a in enumerate(nxt_o):
+                assert beq(nxt[r][:a.data.size], a.data.reshape(-1, order="F")), ("get", k, r)
         cur_o = nxt_o
 
 
