@@ -231,6 +231,8 @@ def run_b200(args):
     ts = [pa.Transposition(uy, ux, method=method), pa.Transposition(uz, uy, method=method),
           pa.Transposition(uy, uz, method=method), pa.Transposition(ux, uy, method=method)]
     overlap = not args.no_overlap
+    if args.remote_ctas is not None:
+        pa.check(pa.lib.pa_set_tunable(b"remote_ctas", args.remote_ctas))
 
     def barrier():
         torch.cuda.synchronize()
@@ -359,6 +361,7 @@ def run_b200(args):
             if t.dim is None:
                 continue
             t.enable_timing(True)
+            barrier()  # ranks enter together: otherwise the sections contain the skew
             pa.transpose_(t, waitall=True, overlap=False)
             tm = t.timings()
             t.enable_timing(False)
@@ -452,6 +455,8 @@ def main():
     ap.add_argument("--method", default="pointtopoint",
                     choices=["pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--remote-ctas", type=int, default=None,
+                    help="grid cap of the PeerPut/PeerGet kernels (tunable remote_ctas)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.gpus not in (1, 2, 4, 8):

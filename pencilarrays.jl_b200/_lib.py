@@ -74,6 +74,7 @@ SIGNATURES = {
     "pa_launch_count": (C.c_int64, []),
     "pa_device_count": (C.c_int, []),
     "pa_set_device": (C.c_int, [C.c_int]),
+    "pa_set_tunable": (C.c_int, [C.c_char_p, C.c_int64]),
     "pa_dims_create": (C.c_int, [C.c_int, C.c_int, _I64P]),
     "pa_topology_create": (C.c_int, [C.c_int, _I64P, C.c_int, C.POINTER(_P)]),
     "pa_topology_destroy": (None, [_P]),

@@ -48,6 +48,17 @@ pa_status pa_set_device(int device) {
   return set_device(device);
 }
 
+pa_status pa_set_tunable(const char* name, int64_t value) {
+  if (!name) return PA_EINVAL;
+  if (!strcmp(name, "remote_ctas")) g_tun.remote_ctas = (int)value;
+  else if (!strcmp(name, "box_copy_ctas")) g_tun.box_copy_ctas = (int)value;
+  else {
+    set_error("unknown tunable '%s'", name);
+    return PA_EINVAL;
+  }
+  return PA_OK;
+}
+
 // ---- topology -----------------------------------------------------------------
 pa_status pa_dims_create(int nprocs, int M, int64_t* dims) {
   if (nprocs < 1 || M < 1 || M > PA_MAX_TOPO || !dims) {
@@ -446,7 +457,7 @@ pa_status pa_box_copy(int nd, const int64_t* extent, const int64_t* src_stride,
   if (src || dst) {
     s = need_gpu();
     if (s != PA_OK) return s;
-    s = launch_block(b, src, dst, stream, &vec);
+    s = launch_block(b, src, dst, stream, &vec, g_tun.box_copy_ctas);
   }
   if (chosen) {
     export_block(b, chosen);

@@ -26,6 +26,7 @@
 
 namespace pa {
 
+Tunables g_tun;
 static std::atomic<i64> g_launches{0};
 i64 launch_count() { return g_launches.load(); }
 
@@ -37,6 +38,7 @@ struct KParams {
   long long ex, ey;                  // tile-dim extents (k_rows: ex in vectors)
   long long sx_s, sx_d, sy_s, sy_d;  // byte strides of X and Y
   unsigned tiles_x, tiles_y;
+  unsigned long long total;  // tiles in the launch; CTAs stride over them when the grid is capped
   int no;  // outer dims
   long long oe[MAXO], os[MAXO], od[MAXO];
   int lx_log2, ux_log2;  // k_rows thread/unroll shape
@@ -76,13 +78,14 @@ template <typename VT>
 __global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p) {
   constexpr int W = sizeof(VT);
   constexpr int U = 8;
-  unsigned tx, ty;
-  const char* s;
-  char* d;
-  decode_tile(p, blockIdx.x, tx, ty, s, d);
   const int lxl = p.lx_log2, uxl = p.ux_log2;
   const int LX = 1 << lxl, LY = 256 >> lxl;
   const int lx = threadIdx.x & (LX - 1), ly = threadIdx.x >> lxl;
+  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
+  unsigned tx, ty;
+  const char* s;
+  char* d;
+  decode_tile(p, bid, tx, ty, s, d);
   const long long xv0 = (long long)tx * ((long long)LX << uxl) + lx;
   const long long y0 = (long long)ty * ((long long)LY << (3 - uxl)) + ly;
   VT v[U];
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p)
 #pragma unroll
   for (int i = 0; i < U; ++i)
     if (ok[i]) st_stream<VT>(d + dof[i], v[i]);
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -136,11 +140,12 @@ __global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ K
   constexpr int QI = TBQ / 8;
   __shared__ uint4 sm[TA * PITCH];
 
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
   unsigned tx, ty;
   const char* s;
   char* d;
-  decode_tile(p, blockIdx.x, tx, ty, s, d);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  decode_tile(p, bid, tx, ty, s, d);
   const long long x0 = (long long)tx * TA, y0 = (long long)ty * TB;
   const long long xl = x0 + lane * V;
   const bool xok = xl < p.ex;
@@ -171,6 +176,8 @@ __global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ K
     const long long y = y0 + (long long)qq * V;
     if (x < p.ex && y < p.ey) st_stream<uint4>(d + x * p.sx_d + y * S, sm[xr * PITCH + qq]);
   }
+  if (bid + gridDim.x < p.total) __syncthreads();  // shared tile is reused by the next iteration
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -178,11 +185,12 @@ __global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ K
 template <typename ET>
 __global__ void __launch_bounds__(256) k_tile_scalar(const __grid_constant__ KParams p) {
   __shared__ ET sm[32][33];
+  const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
   unsigned tx, ty;
   const char* s;
   char* d;
-  decode_tile(p, blockIdx.x, tx, ty, s, d);
-  const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
+  decode_tile(p, bid, tx, ty, s, d);
   const long long x0 = (long long)tx * 32, y0 = (long long)ty * 32;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -196,6 +204,8 @@ __global__ void __launch_bounds__(256) k_tile_scalar(const __grid_constant__ KPa
     const long long x = x0 + b + 8 * k, y = y0 + a;
     if (x < p.ex && y < p.ey)
       *reinterpret_cast<ET*>(d + x * p.sx_d + y * p.sy_d) = sm[a][b + 8 * k];
+  }
+  if (bid + gridDim.x < p.total) __syncthreads();
   }
 }
 
@@ -214,7 +224,7 @@ static int ceil_log2(long long x) {
 static long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 template <typename K>
-static pa_status do_launch(K kern, const KParams& p, cudaStream_t st) {
+static pa_status do_launch(K kern, KParams& p, cudaStream_t st, int max_ctas) {
   unsigned long long tiles = (unsigned long long)p.tiles_x * p.tiles_y;
   for (int i = 0; i < p.no; ++i) tiles *= (unsigned long long)p.oe[i];
   if (tiles == 0) return PA_OK;
@@ -222,7 +232,10 @@ static pa_status do_launch(K kern, const KParams& p, cudaStream_t st) {
     set_error("block too large for one launch (%llu tiles)", tiles);
     return PA_EINVAL;
   }
-  kern<<<(unsigned)tiles, 256, 0, st>>>(p);
+  p.total = tiles;
+  const unsigned grid = (max_ctas > 0 && tiles > (unsigned long long)max_ctas) ? (unsigned)max_ctas
+                                                                             : (unsigned)tiles;
+  kern<<<grid, 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("kernel launch failed: %s", cudaGetErrorString(e));
@@ -233,7 +246,7 @@ static pa_status do_launch(K kern, const KParams& p, cudaStream_t st) {
 }
 
 pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* stream,
-                       int* vec_used) {
+                       int* vec_used, int max_ctas) {
   if (vec_used) *vec_used = 0;
   if (b.klass == KC_EMPTY) return PA_OK;
   if (!src || !dst) {
@@ -281,11 +294,11 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     p.tiles_y = (unsigned)cdiv(Y.e, LY << (3 - uxl));
     if (vec_used) *vec_used = W;
     switch (W) {
-      case 16: return do_launch(k_rows<uint4>, p, st);
-      case 8: return do_launch(k_rows<uint2>, p, st);
-      case 4: return do_launch(k_rows<uint32_t>, p, st);
-      case 2: return do_launch(k_rows<uint16_t>, p, st);
-      default: return do_launch(k_rows<uint8_t>, p, st);
+      case 16: return do_launch(k_rows<uint4>, p, st, max_ctas);
+      case 8: return do_launch(k_rows<uint2>, p, st, max_ctas);
+      case 4: return do_launch(k_rows<uint32_t>, p, st, max_ctas);
+      case 2: return do_launch(k_rows<uint16_t>, p, st, max_ctas);
+      default: return do_launch(k_rows<uint8_t>, p, st, max_ctas);
     }
   }
 
@@ -295,15 +308,15 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     if (S == 16) {
       p.tiles_x = (unsigned)cdiv(X.e, 32);
       p.tiles_y = (unsigned)cdiv(Y.e, 32);
-      return do_launch(k_transpose_vec<16, 32>, p, st);
+      return do_launch(k_transpose_vec<16, 32>, p, st, max_ctas);
     } else if (S == 8) {
       p.tiles_x = (unsigned)cdiv(X.e, 64);
       p.tiles_y = (unsigned)cdiv(Y.e, 64);
-      return do_launch(k_transpose_vec<8, 32>, p, st);
+      return do_launch(k_transpose_vec<8, 32>, p, st, max_ctas);
     } else {
       p.tiles_x = (unsigned)cdiv(X.e, 128);
       p.tiles_y = (unsigned)cdiv(Y.e, 64);
-      return do_launch(k_transpose_vec<4, 16>, p, st);
+      return do_launch(k_transpose_vec<4, 16>, p, st, max_ctas);
     }
   }
 
@@ -312,11 +325,11 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
   p.tiles_y = (unsigned)cdiv(Y.e, 32);
   if (vec_used) *vec_used = (int)S;
   switch (S) {
-    case 16: return do_launch(k_tile_scalar<uint4>, p, st);
-    case 8: return do_launch(k_tile_scalar<uint2>, p, st);
-    case 4: return do_launch(k_tile_scalar<uint32_t>, p, st);
-    case 2: return do_launch(k_tile_scalar<uint16_t>, p, st);
-    case 1: return do_launch(k_tile_scalar<uint8_t>, p, st);
+    case 16: return do_launch(k_tile_scalar<uint4>, p, st, max_ctas);
+    case 8: return do_launch(k_tile_scalar<uint2>, p, st, max_ctas);
+    case 4: return do_launch(k_tile_scalar<uint32_t>, p, st, max_ctas);
+    case 2: return do_launch(k_tile_scalar<uint16_t>, p, st, max_ctas);
+    case 1: return do_launch(k_tile_scalar<uint8_t>, p, st, max_ctas);
     default:
       set_error("unsupported element word size %lld", S);
       return PA_EINVAL;

@@ -99,8 +99,17 @@ struct BlockCopy {
 void canonicalize(BlockCopy& b);
 
 // launch on `stream`; src/dst are array base pointers (offsets come from b)
+// max_ctas > 0 caps the grid (CTAs then stride over the tiles): used for the
+// NVLink-bound remote kernels so that they leave SMs to concurrent local work.
 pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* stream,
-                       int* vec_used);
+                       int* vec_used, int max_ctas = 0);
+
+// run-time tunables (pa_set_tunable)
+struct Tunables {
+  int remote_ctas = 0;    // grid cap of put/get kernels (0 = one tile per CTA)
+  int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
+};
+extern Tunables g_tun;
 
 // ---- Transposition plan (Transpositions.jl:69-119, 281-343) ----------------
 struct Peer {

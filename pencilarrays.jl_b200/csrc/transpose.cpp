@@ -485,17 +485,17 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
     if (timing) CU(cudaEventRecord(S.t[2], S.comm_s));
     rc = line_barrier();
     if (rc != PA_OK) return rc;
-    CU(cudaEventRecord(S.ev_recvd[0], S.comm_s));
-    CU(cudaStreamWaitEvent(S.pack_s, S.ev_recvd[0], 0));
+    // fence, remote kernels and closing fence run in order on the high-priority
+    // comm stream; the remote kernels' grid is capped (g_tun.remote_ctas) so the
+    // self block on the low-priority stream keeps SMs while NVLink is the limit
     for (int k = 1; k < nproc; ++k) {
       const int to = (me + k) % nproc, from = (me - k + nproc) % nproc;
-      rc = get ? launch_block(P->peers[from].get, win[from], dst, S.pack_s, nullptr)
-               : launch_block(P->peers[to].put, src, win[to], S.pack_s, nullptr);
+      rc = get ? launch_block(P->peers[from].get, win[from], dst, S.comm_s, nullptr, g_tun.remote_ctas)
+               : launch_block(P->peers[to].put, src, win[to], S.comm_s, nullptr, g_tun.remote_ctas);
       if (rc != PA_OK) return rc;
     }
-    CU(cudaEventRecord(S.ev_allpacked, S.pack_s));
-    if (timing) CU(cudaEventRecord(S.t[1], S.pack_s));
-    CU(cudaStreamWaitEvent(S.comm_s, S.ev_allpacked, 0));
+    CU(cudaEventRecord(S.ev_allpacked, S.comm_s));
+    if (timing) CU(cudaEventRecord(S.t[1], S.comm_s));
     rc = line_barrier();
     if (rc != PA_OK) return rc;
     CU(cudaEventRecord(S.ev_comm_done, S.comm_s));

@@ -102,6 +102,38 @@ def main():
                                                           lambda: launch(e, s_, d_, 16, a1, b0, 1)], [0, 1]))
     rec("k_transpose_vec<16> GET both directions", timeit([lambda: launch(e, s_, d_, 16, a1, b0, 0),
                                                           lambda: launch(e, s_, d_, 16, a0, b1, 1)], [0, 1]))
+    # ---- grid cap sweep: how many CTAs does an NVLink-bound kernel need? ----
+    def cap(n):
+        check(lib.pa_set_tunable(b"box_copy_ctas", n))
+
+    for c in (37, 74, 148, 296, 592, 1184, 0):
+        cap(c)
+        rec(f"k_transpose_vec<16> PUT grid cap {c}", timeit([lambda: launch(e, s_, d_, 16, a0, b1, 0)], [0]))
+        rec(f"k_transpose_vec<16> GET grid cap {c}", timeit([lambda: launch(e, s_, d_, 16, a1, b0, 0)], [0]))
+        rec(f"k_rows PUT contiguous grid cap {c}", timeit([lambda: launch([nel], [1], [1], 16, a0, b1, 0)], [0]))
+    cap(0)
+    # ---- remote kernel (high-priority stream, capped) beside a local transpose (low priority) ----
+    import time
+    hi = torch.cuda.Stream(device=0, priority=-1)
+    lo = torch.cuda.Stream(device=0, priority=0)
+    c0 = torch.empty(N, dtype=torch.uint8, device="cuda:0")
+    for c in (0, 148, 296, 592):
+        def both():
+            with torch.cuda.stream(lo):
+                cap(0)
+                launch(e, s_, d_, 16, a0, c0, 0)     # local K3-like transpose: 2 GiB of HBM traffic
+            with torch.cuda.stream(hi):
+                cap(c)
+                launch(e, s_, d_, 16, a0, b1, 0)     # put of 1 GiB
+        both()
+        torch.cuda.synchronize(0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            both()
+            torch.cuda.synchronize(0)
+        ms = (time.perf_counter() - t0) * 100
+        rec(f"local transpose (lo prio) || PUT (hi prio, cap {c}) wall", ms)
+    cap(0)
     # f32 transposes (cfg5-like)
     e, s_, d_ = [512, 512, 1024], [1, 512, 262144], [512, 1, 262144]
     rec("k_transpose_vec<4> PUT", timeit([lambda: launch(e, s_, d_, 4, a0, b1, 0)], [0]))
