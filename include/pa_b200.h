@@ -87,8 +87,8 @@ int64_t pa_launch_count(void);
 int pa_device_count(void);
 /* run-time tunables: "remote_ctas" = grid cap of the PeerPut/PeerGet kernels
  * (they are NVLink-bound; a capped, tile-striding grid leaves SMs to the local
- * kernels running beside them; 0 = uncapped), "box_copy_ctas" = same cap for
- * pa_box_copy (benchmarks).                                                   */
+ * kernels running beside them; n > 0 = n CTAs, n < 0 = |n| CTAs per SM (default
+ * -4), 0 = uncapped), "box_copy_ctas" = same cap for pa_box_copy (benchmarks). */
 pa_status pa_set_tunable(const char* name, int64_t value);
 /* bind the calling thread to a device (one process per GPU: LOCAL_RANK).  All
  * handles created afterwards (streams, staging arenas, communicator) live there. */

@@ -2,13 +2,14 @@
 //
 // Every data movement of the path -- K1 pack (copy_range!,
 // Transpositions.jl:552-583), K2 unpack+permute (copy_permuted! ->
-// _permutedims!, :585-664), K3 fused self block / permute_local! (:235-270) --
-// is one primitive: an N-d strided box copy
+// _permutedims!, :585-664), K3 fused self block / permute_local! (:235-270),
+// and the one-sided K1-put / K2-get variants whose other side is a peer GPU's
+// memory over NVLink -- is one primitive: an N-d strided box copy
 //     dst[sum k_i ds_i] = src[sum k_i ss_i],  k in box,
 // canonicalised on the host (plan.cpp) into tile dims X (source-fastest),
 // Y (destination-fastest, or the next dim) and up to 6 outer dims.
 //
-// Three kernels, all HBM-bound, all pure byte movers (bit-exact by construction):
+// Three kernels, all bandwidth-bound pure byte movers (bit-exact by construction):
 //   k_rows<VT>          X contiguous on both sides: vectorised row copy, 8 x
 //                       128-bit loads in flight per thread, streaming hints.
 //   k_transpose_vec<S>  X contiguous in src, Y contiguous in dst: 512-byte
@@ -17,6 +18,10 @@
 //                       512-byte coalesced 128-bit stores.
 //   k_tile_scalar<ET>   any strides / alignment (odd sizes, tiny boxes):
 //                       32x32 element tile through padded shared memory.
+// Each exists in two flavours: LOOP=false, one tile per CTA (HBM-bound local
+// work: the grid is the whole problem), and LOOP=true, a capped grid whose CTAs
+// stride over the tiles (NVLink-bound remote work: a few CTAs per SM saturate
+// the links and the rest of the SM stays available to concurrent local kernels).
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -38,8 +43,8 @@ struct KParams {
   long long ex, ey;                  // tile-dim extents (k_rows: ex in vectors)
   long long sx_s, sx_d, sy_s, sy_d;  // byte strides of X and Y
   unsigned tiles_x, tiles_y;
-  unsigned long long total;  // tiles in the launch; CTAs stride over them when the grid is capped
-  int no;  // outer dims
+  unsigned long long total;  // tiles in the launch
+  int no;                    // outer dims
   long long oe[MAXO], os[MAXO], od[MAXO];
   int lx_log2, ux_log2;  // k_rows thread/unroll shape
 };
@@ -75,13 +80,12 @@ __device__ __forceinline__ void st_stream(char* p, const T& v) {
 // K_rows: runs contiguous on both sides.
 // 256 threads as LX x LY, each thread moves 8 vectors laid out UX x UY.
 template <typename VT>
-__global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p) {
+__device__ __forceinline__ void rows_tile(const KParams& p, unsigned long long bid) {
   constexpr int W = sizeof(VT);
   constexpr int U = 8;
   const int lxl = p.lx_log2, uxl = p.ux_log2;
   const int LX = 1 << lxl, LY = 256 >> lxl;
   const int lx = threadIdx.x & (LX - 1), ly = threadIdx.x >> lxl;
-  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
   unsigned tx, ty;
   const char* s;
   char* d;
@@ -105,6 +109,14 @@ __global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p)
 #pragma unroll
   for (int i = 0; i < U; ++i)
     if (ok[i]) st_stream<VT>(d + dof[i], v[i]);
+}
+
+template <typename VT, bool LOOP>
+__global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p) {
+  if constexpr (LOOP) {
+    for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) rows_tile<VT>(p, bid);
+  } else {
+    rows_tile<VT>(p, blockIdx.x);
   }
 }
 
@@ -132,16 +144,13 @@ __device__ __forceinline__ uint4 gather_col<4>(const uint4 (&r)[4], int c) {
 }
 
 template <int S, int TBQ>
-__global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ KParams p) {
+__device__ __forceinline__ void transpose_tile(const KParams& p, unsigned long long bid, uint4* sm) {
   constexpr int V = 16 / S;
   constexpr int TA = 32 * V;
   constexpr int TB = TBQ * V;
   constexpr int PITCH = TBQ + 1;  // odd pitch in 16-byte items: conflict-free both phases
   constexpr int QI = TBQ / 8;
-  __shared__ uint4 sm[TA * PITCH];
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
   unsigned tx, ty;
   const char* s;
   char* d;
@@ -176,17 +185,26 @@ __global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ K
     const long long y = y0 + (long long)qq * V;
     if (x < p.ex && y < p.ey) st_stream<uint4>(d + x * p.sx_d + y * S, sm[xr * PITCH + qq]);
   }
-  if (bid + gridDim.x < p.total) __syncthreads();  // shared tile is reused by the next iteration
+}
+
+template <int S, int TBQ, bool LOOP>
+__global__ void __launch_bounds__(256) k_transpose_vec(const __grid_constant__ KParams p) {
+  __shared__ uint4 sm[(32 * 16 / S) * (TBQ + 1)];
+  if constexpr (LOOP) {
+    for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
+      transpose_tile<S, TBQ>(p, bid, sm);
+      __syncthreads();  // the shared tile is reused by the next iteration
+    }
+  } else {
+    transpose_tile<S, TBQ>(p, blockIdx.x, sm);
   }
 }
 
 // ---------------------------------------------------------------------------
 // K_tile_scalar: general strides, element-wise accesses.
 template <typename ET>
-__global__ void __launch_bounds__(256) k_tile_scalar(const __grid_constant__ KParams p) {
-  __shared__ ET sm[32][33];
+__device__ __forceinline__ void scalar_tile(const KParams& p, unsigned long long bid, ET (*sm)[33]) {
   const int a = threadIdx.x & 31, b = threadIdx.x >> 5;
-  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
   unsigned tx, ty;
   const char* s;
   char* d;
@@ -205,7 +223,18 @@ __global__ void __launch_bounds__(256) k_tile_scalar(const __grid_constant__ KPa
     if (x < p.ex && y < p.ey)
       *reinterpret_cast<ET*>(d + x * p.sx_d + y * p.sy_d) = sm[a][b + 8 * k];
   }
-  if (bid + gridDim.x < p.total) __syncthreads();
+}
+
+template <typename ET, bool LOOP>
+__global__ void __launch_bounds__(256) k_tile_scalar(const __grid_constant__ KParams p) {
+  __shared__ ET sm[32][33];
+  if constexpr (LOOP) {
+    for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
+      scalar_tile<ET>(p, bid, sm);
+      __syncthreads();
+    }
+  } else {
+    scalar_tile<ET>(p, blockIdx.x, sm);
   }
 }
 
@@ -223,8 +252,20 @@ static int ceil_log2(long long x) {
 }
 static long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
-template <typename K>
-static pa_status do_launch(K kern, KParams& p, cudaStream_t st, int max_ctas) {
+static int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess)
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+// max_ctas: 0 = one tile per CTA; > 0 = capped, tile-striding grid;
+//           < 0 = -max_ctas CTAs per SM (resolved against the device here)
+template <typename K1, typename KL>
+static pa_status do_launch(K1 kern_one, KL kern_loop, KParams& p, cudaStream_t st, int max_ctas) {
   unsigned long long tiles = (unsigned long long)p.tiles_x * p.tiles_y;
   for (int i = 0; i < p.no; ++i) tiles *= (unsigned long long)p.oe[i];
   if (tiles == 0) return PA_OK;
@@ -233,9 +274,11 @@ static pa_status do_launch(K kern, KParams& p, cudaStream_t st, int max_ctas) {
     return PA_EINVAL;
   }
   p.total = tiles;
-  const unsigned grid = (max_ctas > 0 && tiles > (unsigned long long)max_ctas) ? (unsigned)max_ctas
-                                                                             : (unsigned)tiles;
-  kern<<<grid, 256, 0, st>>>(p);
+  if (max_ctas < 0) max_ctas = -max_ctas * sm_count();
+  if (max_ctas > 0 && tiles > (unsigned long long)max_ctas)
+    kern_loop<<<(unsigned)max_ctas, 256, 0, st>>>(p);
+  else
+    kern_one<<<(unsigned)tiles, 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("kernel launch failed: %s", cudaGetErrorString(e));
@@ -244,6 +287,8 @@ static pa_status do_launch(K kern, KParams& p, cudaStream_t st, int max_ctas) {
   g_launches.fetch_add(1);
   return PA_OK;
 }
+
+#define LAUNCH(K, ...) do_launch(K<__VA_ARGS__, false>, K<__VA_ARGS__, true>, p, st, max_ctas)
 
 pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* stream,
                        int* vec_used, int max_ctas) {
@@ -294,11 +339,11 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     p.tiles_y = (unsigned)cdiv(Y.e, LY << (3 - uxl));
     if (vec_used) *vec_used = W;
     switch (W) {
-      case 16: return do_launch(k_rows<uint4>, p, st, max_ctas);
-      case 8: return do_launch(k_rows<uint2>, p, st, max_ctas);
-      case 4: return do_launch(k_rows<uint32_t>, p, st, max_ctas);
-      case 2: return do_launch(k_rows<uint16_t>, p, st, max_ctas);
-      default: return do_launch(k_rows<uint8_t>, p, st, max_ctas);
+      case 16: return LAUNCH(k_rows, uint4);
+      case 8: return LAUNCH(k_rows, uint2);
+      case 4: return LAUNCH(k_rows, uint32_t);
+      case 2: return LAUNCH(k_rows, uint16_t);
+      default: return LAUNCH(k_rows, uint8_t);
     }
   }
 
@@ -308,15 +353,15 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     if (S == 16) {
       p.tiles_x = (unsigned)cdiv(X.e, 32);
       p.tiles_y = (unsigned)cdiv(Y.e, 32);
-      return do_launch(k_transpose_vec<16, 32>, p, st, max_ctas);
+      return LAUNCH(k_transpose_vec, 16, 32);
     } else if (S == 8) {
       p.tiles_x = (unsigned)cdiv(X.e, 64);
       p.tiles_y = (unsigned)cdiv(Y.e, 64);
-      return do_launch(k_transpose_vec<8, 32>, p, st, max_ctas);
+      return LAUNCH(k_transpose_vec, 8, 32);
     } else {
       p.tiles_x = (unsigned)cdiv(X.e, 128);
       p.tiles_y = (unsigned)cdiv(Y.e, 64);
-      return do_launch(k_transpose_vec<4, 16>, p, st, max_ctas);
+      return LAUNCH(k_transpose_vec, 4, 16);
     }
   }
 
@@ -325,11 +370,11 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
   p.tiles_y = (unsigned)cdiv(Y.e, 32);
   if (vec_used) *vec_used = (int)S;
   switch (S) {
-    case 16: return do_launch(k_tile_scalar<uint4>, p, st, max_ctas);
-    case 8: return do_launch(k_tile_scalar<uint2>, p, st, max_ctas);
-    case 4: return do_launch(k_tile_scalar<uint32_t>, p, st, max_ctas);
-    case 2: return do_launch(k_tile_scalar<uint16_t>, p, st, max_ctas);
-    case 1: return do_launch(k_tile_scalar<uint8_t>, p, st, max_ctas);
+    case 16: return LAUNCH(k_tile_scalar, uint4);
+    case 8: return LAUNCH(k_tile_scalar, uint2);
+    case 4: return LAUNCH(k_tile_scalar, uint32_t);
+    case 2: return LAUNCH(k_tile_scalar, uint16_t);
+    case 1: return LAUNCH(k_tile_scalar, uint8_t);
     default:
       set_error("unsupported element word size %lld", S);
       return PA_EINVAL;

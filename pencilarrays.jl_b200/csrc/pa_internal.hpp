@@ -106,7 +106,8 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
 
 // run-time tunables (pa_set_tunable)
 struct Tunables {
-  int remote_ctas = 0;    // grid cap of put/get kernels (0 = one tile per CTA)
+  int remote_ctas = -4;   // grid cap of put/get kernels: n > 0 CTAs, n < 0 = |n| per SM, 0 = uncapped
+                          // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
 };
 extern Tunables g_tun;
