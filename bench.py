@@ -226,13 +226,34 @@ def run_b200(args):
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
     ux.data.view(torch.float64).normal_(generator=gen)
     orig = ux.data.clone()
-    method = {"alltoallv": pa.Alltoallv(), "pointtopoint": pa.PointToPoint(),
-              "peerput": pa.PeerPut(), "peerget": pa.PeerGet()}[args.method]
-    ts = [pa.Transposition(uy, ux, method=method), pa.Transposition(uz, uy, method=method),
-          pa.Transposition(uy, uz, method=method), pa.Transposition(ux, uy, method=method)]
+    methods = {"alltoallv": pa.Alltoallv(), "pointtopoint": pa.PointToPoint(),
+               "peerput": pa.PeerPut(), "peerget": pa.PeerGet()}
+    # auto: the one-sided put path over NVLink (fastest, profiles/r1_bench_n8_*.json); if the
+    # CUDA-IPC window cannot be set up on ANY rank, every rank takes the NCCL PointToPoint path
+    name = ("peerput" if n > 1 else "pointtopoint") if args.method == "auto" else args.method
+    pairs = [(uy, ux), (uz, uy), (uy, uz), (ux, uy)]
+    while True:
+        method = methods[name]
+        ok_here = 1
+        try:
+            ts = [pa.Transposition(d, s, method=method) for d, s in pairs]
+        except pa.PencilError as e:  # e.g. IPC not permitted in this container
+            ok_here, ts = 0, None
+            print(f"[rank {rank}] {name} unavailable: {e}", file=sys.stderr)
+        if n > 1:
+            flag = torch.tensor([ok_here], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok_here = int(flag.item())
+        if ok_here:
+            break
+        if args.method != "auto" or name == "pointtopoint":
+            raise SystemExit(f"method {name} could not be set up")
+        name = "pointtopoint"
     overlap = not args.no_overlap
     if args.remote_ctas is not None:
         pa.check(pa.lib.pa_set_tunable(b"remote_ctas", args.remote_ctas))
+    if args.nccl_fences:
+        pa.check(pa.lib.pa_set_tunable(b"nccl_fences", 1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -452,9 +473,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--method", default="pointtopoint",
-                    choices=["pointtopoint", "alltoallv", "peerput", "peerget"])
+    ap.add_argument("--method", default="auto",
+                    choices=["auto", "pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--nccl-fences", action="store_true",
+                    help="one-sided methods: fence with NCCL groups instead of NVLink flags")
     ap.add_argument("--remote-ctas", type=int, default=None,
                     help="grid cap of the PeerPut/PeerGet kernels (tunable remote_ctas)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -227,6 +227,13 @@ pa_status pa_box_copy(int nd, const int64_t* extent, const int64_t* src_stride,
 pa_status pa_comm_unique_id(void* id128);
 pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** out);
 void pa_comm_destroy(pa_comm* c);
+/* Optional flag window of the one-sided methods: each rank exports a small
+ * device buffer (one 64-bit word per source rank) and imports everybody
+ * else's; the fences of PA_PEER_PUT / PA_PEER_GET then become one tiny kernel
+ * (st.release.sys to the peers + ld.acquire.sys polling, 10 s time-out) instead
+ * of an NCCL send/recv group.  Without it the NCCL fences are used.           */
+pa_status pa_comm_flags_export(pa_comm* c, void* handle64, int64_t* offset);
+pa_status pa_comm_flags_import(pa_comm* c, int rank, const void* handle64, int64_t offset);
 
 /* ---- PeerPut windows (PA_PEER_PUT) -----------------------------------------
  * The analogue of a collective MPI_Win_create over `dest`: every rank exports

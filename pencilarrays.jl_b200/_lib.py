@@ -103,6 +103,8 @@ SIGNATURES = {
     "pa_comm_unique_id": (C.c_int, [_P]),
     "pa_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "pa_comm_destroy": (None, [_P]),
+    "pa_comm_flags_export": (C.c_int, [_P, _P, _I64P]),
+    "pa_comm_flags_import": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
     "pa_ipc_export": (C.c_int, [_P, _P, _I64P]),
     "pa_ipc_import": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
     "pa_plan_set_window": (C.c_int, [_P, _P, C.c_int, _P]),

@@ -82,4 +82,21 @@ def comm_world(init_nccl: bool | None = None) -> Comm:
         h = C.c_void_p()
         check(lib.pa_comm_init_rank(obj[0], size, rank, C.byref(h)))
         handle = h
+        # flag window for the NVLink fences of PeerPut / PeerGet (optional: on any
+        # failure every rank keeps the NCCL fences)
+        fh = C.create_string_buffer(_lib.PA_IPC_HANDLE_BYTES)
+        off = C.c_int64()
+        ok = lib.pa_comm_flags_export(h, fh, C.byref(off)) == _lib.PA_OK
+        allf = [None] * size
+        dist.all_gather_object(allf, (rank, bytes(fh.raw), off.value, ok))
+        ok = all(o for (_, _, _, o) in allf)
+        if ok:
+            for (r, hh, oo, _) in allf:
+                if r != rank and lib.pa_comm_flags_import(h, r, hh, oo) != _lib.PA_OK:
+                    ok = False
+                    break
+        oks = [None] * size
+        dist.all_gather_object(oks, ok)
+        if not all(oks):  # all ranks must fence the same way
+            check(lib.pa_set_tunable(b"nccl_fences", 1))
     return Comm(rank, size, handle=handle)

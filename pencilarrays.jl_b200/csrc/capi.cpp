@@ -52,6 +52,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   if (!name) return PA_EINVAL;
   if (!strcmp(name, "remote_ctas")) g_tun.remote_ctas = (int)value;
   else if (!strcmp(name, "box_copy_ctas")) g_tun.box_copy_ctas = (int)value;
+  else if (!strcmp(name, "nccl_fences")) g_tun.nccl_fences = (int)value;
   else {
     set_error("unknown tunable '%s'", name);
     return PA_EINVAL;
@@ -480,6 +481,18 @@ pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** o
     if (s != PA_OK) return s;
     *out = new pa_comm{c};
     return PA_OK;
+  })
+}
+
+pa_status pa_comm_flags_export(pa_comm* c, void* handle64, int64_t* offset) {
+  if (!c || !handle64 || !offset) return PA_EINVAL;
+  return comm_flags_export(c->p, handle64, offset);
+}
+
+pa_status pa_comm_flags_import(pa_comm* c, int rank, const void* handle64, int64_t offset) {
+  GUARD({
+    if (!c || !handle64) return PA_EINVAL;
+    return comm_flags_import(c->p, rank, handle64, offset);
   })
 }
 

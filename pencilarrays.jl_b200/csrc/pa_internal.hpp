@@ -109,6 +109,7 @@ struct Tunables {
   int remote_ctas = -4;   // grid cap of put/get kernels: n > 0 CTAs, n < 0 = |n| per SM, 0 = uncapped
                           // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
+  int nccl_fences = 0;    // 1: one-sided paths fence with NCCL groups even when the flag window exists
 };
 extern Tunables g_tun;
 
@@ -159,6 +160,8 @@ struct Comm;
 pa_status comm_unique_id(void* id128);
 pa_status comm_init(const void* id128, int nranks, int rank, Comm** out);
 void comm_destroy(Comm* c);
+pa_status comm_flags_export(Comm* c, void* handle64, i64* offset);
+pa_status comm_flags_import(Comm* c, int rank, const void* handle64, i64 offset);
 
 pa_status transpose(Plan* plan, Comm* comm, const void* src, void* dst, unsigned flags,
                     void* stream);

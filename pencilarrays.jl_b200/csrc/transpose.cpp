@@ -161,7 +161,46 @@ static NcclApi& nccl() {
 struct Comm {
   ncclComm_t comm = nullptr;
   int nranks = 0, rank = 0, device = 0;
+  // Flag window of the one-sided paths: one 64-bit sequence word per source
+  // rank, written by that rank over NVLink (st.release.sys) and polled locally.
+  unsigned long long* flags = nullptr;                // my words, indexed by source rank
+  std::vector<unsigned long long*> peer_flags;        // peers' windows as mapped here
+  std::vector<unsigned long long> seq_with;           // fences issued with each rank so far
+  int* fence_err = nullptr;                           // mapped pinned host word set on time-out
+  bool flags_ready = false;
 };
+
+// ---- NVLink fence: signal + wait among the ranks of one grid line -------------
+constexpr int FENCE_MAX = 64;
+struct FenceParams {
+  int n;
+  unsigned long long* remote[FENCE_MAX];  // peer's word for me
+  unsigned long long* local[FENCE_MAX];   // my word for that peer
+  unsigned long long seq[FENCE_MAX];
+  unsigned long long timeout_ns;
+  int* err;
+};
+
+__global__ void k_fence(const __grid_constant__ FenceParams fp) {
+  const int t = threadIdx.x;
+  if (t >= fp.n) return;
+  // everything this GPU wrote before (puts into peer memory included) is visible
+  // system-wide before the peer can observe the new sequence number
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(fp.remote[t]), "l"(fp.seq[t]) : "memory");
+  unsigned long long t0, now, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(fp.local[t]) : "memory");
+    if (v >= fp.seq[t]) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - t0 > fp.timeout_ns) {  // a peer died: do not hang the GPU
+      *fp.err = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
+}
 
 pa_status comm_unique_id(void* id128) {
   static_assert(sizeof(ncclUniqueId) <= PA_UNIQUE_ID_BYTES, "unique id size");
@@ -199,7 +238,40 @@ pa_status comm_init(const void* id128, int nranks, int rank, Comm** out) {
 void comm_destroy(Comm* c) {
   if (!c) return;
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  if (c->flags) cudaFree(c->flags);
+  if (c->fence_err) cudaFreeHost(c->fence_err);
   delete c;
+}
+
+// flag window: allocate + export (collective exchange is the caller's job)
+pa_status comm_flags_export(Comm* c, void* handle64, i64* offset) {
+  if (!c->flags) {
+    CU(cudaMalloc((void**)&c->flags, sizeof(unsigned long long) * (size_t)c->nranks));
+    CU(cudaMemset(c->flags, 0, sizeof(unsigned long long) * (size_t)c->nranks));
+    CU(cudaHostAlloc((void**)&c->fence_err, sizeof(int), cudaHostAllocMapped));
+    *c->fence_err = 0;
+    CU(cudaDeviceSynchronize());
+    c->peer_flags.assign(c->nranks, nullptr);
+    c->seq_with.assign(c->nranks, 0);
+  }
+  return ipc_export(c->flags, handle64, offset);
+}
+
+pa_status comm_flags_import(Comm* c, int rank, const void* handle64, i64 offset) {
+  if (!c->flags || rank < 0 || rank >= c->nranks) {
+    set_error("flag window: export first / rank out of range");
+    return PA_ESTATE;
+  }
+  if (rank == c->rank) return PA_OK;
+  void* p = nullptr;
+  pa_status s = ipc_import(handle64, offset, &p);
+  if (s != PA_OK) return s;
+  c->peer_flags[rank] = (unsigned long long*)p;
+  bool all = true;
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && !c->peer_flags[r]) all = false;
+  c->flags_ready = all;
+  return PA_OK;
 }
 
 // ---- staging arenas ----------------------------------------------------------
@@ -467,6 +539,30 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
         return PA_ESTATE;
       }
     auto line_barrier = [&]() -> pa_status {
+      if (comm->flags_ready && !g_tun.nccl_fences) {
+        // NVLink flag fence: one tiny kernel signals every peer of the line and
+        // waits for their signals (a few microseconds instead of an NCCL group)
+        if (*comm->fence_err) {
+          set_error("an NVLink fence timed out earlier: a peer rank is gone");
+          return PA_ECUDA;
+        }
+        for (int base = 1; base < nproc; base += FENCE_MAX) {
+          FenceParams fp;
+          fp.n = 0;
+          for (int k = base; k < nproc && fp.n < FENCE_MAX; ++k) {
+            const int wr = P->peers[(me + k) % nproc].world_rank;
+            fp.remote[fp.n] = comm->peer_flags[wr] + comm->rank;
+            fp.local[fp.n] = comm->flags + wr;
+            fp.seq[fp.n] = ++comm->seq_with[wr];
+            ++fp.n;
+          }
+          fp.timeout_ns = 10ull * 1000 * 1000 * 1000;
+          fp.err = comm->fence_err;
+          k_fence<<<1, FENCE_MAX, 0, S.comm_s>>>(fp);
+          CU(cudaGetLastError());
+        }
+        return PA_OK;
+      }
       NC(nccl().GroupStart());
       for (int k = 1; k < nproc; ++k) {
         const int to = (me + k) % nproc, from = (me - k + nproc) % nproc;

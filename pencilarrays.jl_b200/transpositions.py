@@ -140,18 +140,35 @@ def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
     _stream_ptr()  # binds the library to torch's current device
     h = C.create_string_buffer(_lib.PA_IPC_HANDLE_BYTES)
     off = C.c_int64()
-    check(lib.pa_ipc_export(C.c_void_p(lo), h, C.byref(off)))
+    # failures must not leave the other ranks stuck in the collectives below:
+    # every rank always takes part in both exchanges and all raise together
+    err = None
+    st = lib.pa_ipc_export(C.c_void_p(lo), h, C.byref(off))
+    if st != _lib.PA_OK:
+        err = f"rank {comm.rank}: export failed: {lib.pa_last_error().decode()}"
     allh = [None] * comm.size
-    dist.all_gather_object(allh, (comm.rank, bytes(h.raw), off.value))
-    byrank = {r: (hh, oo) for (r, hh, oo) in allh}
-    for n in range(1, plan.info.nproc + 1):
-        peer = plan.peer(n)
-        if peer.is_self:
-            continue
-        hh, oo = byrank[peer.world_rank]
-        mapped = C.c_void_p()
-        check(lib.pa_ipc_import(hh, oo, C.byref(mapped)))
-        check(lib.pa_plan_set_window(plan.h, C.c_void_p(lo), n, mapped))
+    dist.all_gather_object(allh, (comm.rank, bytes(h.raw), off.value, err))
+    errs = [e for (_, _, _, e) in allh if e]
+    if not errs:
+        byrank = {r: (hh, oo) for (r, hh, oo, _) in allh}
+        for n in range(1, plan.info.nproc + 1):
+            peer = plan.peer(n)
+            if peer.is_self:
+                continue
+            hh, oo = byrank[peer.world_rank]
+            mapped = C.c_void_p()
+            st = lib.pa_ipc_import(hh, oo, C.byref(mapped))
+            if st == _lib.PA_OK:
+                st = lib.pa_plan_set_window(plan.h, C.c_void_p(lo), n, mapped)
+            if st != _lib.PA_OK:
+                err = f"rank {comm.rank}: import from rank {peer.world_rank} failed: " \
+                      f"{lib.pa_last_error().decode()}"
+                break
+    oks = [None] * comm.size
+    dist.all_gather_object(oks, err)
+    errs += [e for e in oks if e]
+    if errs:
+        raise _lib.DeviceError(_lib.PA_ECUDA, "one-sided window setup failed: " + "; ".join(errs[:3]))
     reg[id(Ao)] = (weakref.ref(Ao), lo)
 
 
