@@ -53,6 +53,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   if (!strcmp(name, "remote_ctas")) g_tun.remote_ctas = (int)value;
   else if (!strcmp(name, "box_copy_ctas")) g_tun.box_copy_ctas = (int)value;
   else if (!strcmp(name, "nccl_fences")) g_tun.nccl_fences = (int)value;
+  else if (!strcmp(name, "bulk_rows")) g_tun.bulk_rows = (int)value;
   else {
     set_error("unknown tunable '%s'", name);
     return PA_EINVAL;

@@ -121,6 +121,97 @@ __global__ void __launch_bounds__(256) k_rows(const __grid_constant__ KParams p)
 }
 
 // ---------------------------------------------------------------------------
+// K_rows_bulk: the row copy as a pure DMA pipeline (TMA bulk copies, SASS
+// UBLKCP).  One elected thread per CTA drives a ring of STAGES shared-memory
+// buffers: cp.async.bulk global->shared completing on an mbarrier, then
+// cp.async.bulk shared->global in a bulk group; the CTA strides over
+// (row, chunk) units.  No registers or LSU slots are spent on the payload, and
+// the stores leave the SM as whole bulk transactions -- which is what the
+// NVLink-bound put path wants.
+constexpr int BULK_STAGES = 4;
+constexpr int BULK_CHUNK = 16384;  // bytes per stage
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+
+__global__ void __launch_bounds__(32) k_rows_bulk(const __grid_constant__ KParams p) {
+  extern __shared__ __align__(128) char bulk_smem[];
+  __shared__ __align__(8) unsigned long long full[BULK_STAGES];
+  if (threadIdx.x != 0) return;  // a single thread owns the whole pipeline
+  const unsigned chunk = (unsigned)p.lx_log2;  // bytes per unit (<= BULK_CHUNK), multiple of 16
+  const long long run = p.ex;                  // bytes per row
+  for (int s = 0; s < BULK_STAGES; ++s)
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[s])));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+
+  auto unit = [&](unsigned long long bid, const char*& s, char*& d, unsigned& bytes) {
+    unsigned tx, ty;
+    decode_tile(p, bid, tx, ty, s, d);
+    const long long x = (long long)tx * chunk;
+    s += (long long)ty * p.sy_s + x;
+    d += (long long)ty * p.sy_d + x;
+    bytes = (unsigned)((run - x) < (long long)chunk ? (run - x) : (long long)chunk);
+  };
+  auto load = [&](int st, unsigned long long bid) {
+    const char* s;
+    char* d;
+    unsigned bytes;
+    unit(bid, s, d, bytes);
+    const unsigned bar = smem_u32(&full[st]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(bulk_smem + st * BULK_CHUNK)),
+        "l"(s), "r"(bytes), "r"(bar)
+        : "memory");
+  };
+
+  unsigned long long next_load = blockIdx.x;
+  int ls = 0;
+  for (int i = 0; i < BULK_STAGES && next_load < p.total; ++i) {
+    load(ls, next_load);
+    next_load += gridDim.x;
+    ls = (ls + 1) % BULK_STAGES;
+  }
+  int ss = 0, prev = -1;
+  unsigned parity = 0;
+  for (unsigned long long bid = blockIdx.x; bid < p.total; bid += gridDim.x) {
+    const unsigned bar = smem_u32(&full[ss]);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+    const char* s;
+    char* d;
+    unsigned bytes;
+    unit(bid, s, d, bytes);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d),
+                 "r"(smem_u32(bulk_smem + ss * BULK_CHUNK)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (prev >= 0 && next_load < p.total) {
+      // the PREVIOUS stage may be refilled once its store has finished READING it
+      // (all but the newest bulk group done reading)
+      asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      load(prev, next_load);
+      next_load += gridDim.x;
+    }
+    prev = ss;
+    ss = (ss + 1) % BULK_STAGES;
+    if (ss == 0) parity ^= 1;
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
 // K_transpose_vec: element size S in {4,8,16}, V = 16/S elements per vector.
 // Tile: TA = 32*V elements along X (512 B of source row), TB = TBQ*V elements
 // along Y (TBQ*16 B of destination row).
@@ -324,6 +415,36 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     p.oe[i] = b.d[i + 2].e;
     p.os[i] = b.d[i + 2].ss * S;
     p.od[i] = b.d[i + 2].ds * S;
+  }
+
+  if (b.klass == KC_ROWS && g_tun.bulk_rows && std::min(b.stride_align, pal) == 16) {
+    // TMA bulk-copy pipeline (tunable "bulk_rows")
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_rows_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           BULK_STAGES * BULK_CHUNK);
+      attr_set = true;
+    }
+    const long long run = X.e * S;
+    const long long chunk = std::min<long long>(BULK_CHUNK, run);
+    p.ex = run;
+    p.lx_log2 = (int)chunk;
+    p.tiles_x = (unsigned)cdiv(run, chunk);
+    p.tiles_y = (unsigned)Y.e;
+    unsigned long long units = (unsigned long long)p.tiles_x * p.tiles_y;
+    for (int i = 0; i < p.no; ++i) units *= (unsigned long long)p.oe[i];
+    p.total = units;
+    long long ctas = max_ctas > 0 ? max_ctas : (max_ctas < 0 ? -max_ctas : 3) * (long long)sm_count();
+    if ((unsigned long long)ctas > units) ctas = (long long)units;
+    if (vec_used) *vec_used = 16;
+    k_rows_bulk<<<(unsigned)ctas, 32, BULK_STAGES * BULK_CHUNK, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("kernel launch failed: %s", cudaGetErrorString(e));
+      return PA_ECUDA;
+    }
+    g_launches.fetch_add(1);
+    return PA_OK;
   }
 
   if (b.klass == KC_ROWS) {

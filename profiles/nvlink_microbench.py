@@ -134,6 +134,19 @@ def main():
         ms = (time.perf_counter() - t0) * 100
         rec(f"local transpose (lo prio) || PUT (hi prio, cap {c}) wall", ms)
     cap(0)
+    # ---- TMA bulk-copy pipeline (k_rows_bulk, tunable bulk_rows) ----
+    check(lib.pa_set_tunable(b"bulk_rows", 1))
+    e4, s4, d4 = [256, 256 * 1024], [1, 1024], [1, 256]
+    for c in (148, 296, 444, 592, 888):
+        cap(c)
+        rec(f"k_rows_bulk local contiguous, {c} CTAs", timeit([lambda: launch([nel], [1], [1], 16, a0, b0, 0)], [0]))
+        rec(f"k_rows_bulk PUT contiguous, {c} CTAs", timeit([lambda: launch([nel], [1], [1], 16, a0, b1, 0)], [0]))
+        rec(f"k_rows_bulk GET contiguous, {c} CTAs", timeit([lambda: launch([nel], [1], [1], 16, a1, b0, 0)], [0]))
+        rec(f"k_rows_bulk PUT 4KiB runs, {c} CTAs", timeit([lambda: launch(e4, s4, d4, 16, big0, b1, 0)], [0]))
+        rec(f"k_rows_bulk PUT both directions, {c} CTAs",
+            timeit([lambda: launch([nel], [1], [1], 16, a0, b1, 0), lambda: launch([nel], [1], [1], 16, a1, b0, 1)], [0, 1]))
+    cap(0)
+    check(lib.pa_set_tunable(b"bulk_rows", 0))
     # f32 transposes (cfg5-like)
     e, s_, d_ = [512, 512, 1024], [1, 512, 262144], [512, 1, 262144]
     rec("k_transpose_vec<4> PUT", timeit([lambda: launch(e, s_, d_, 4, a0, b1, 0)], [0]))

@@ -131,12 +131,16 @@ def main():
             O.transpose_all(o1, o0)
             o2 = [O.OArray.undef(dtype, po) for po in opens[2]]
             O.transpose_all(o2, o1)
-            pa.transpose_(A[2], A[1])
-            pa.transpose_(A[3], A[2])
-            torch.cuda.synchronize()
-            got = A[3].data.view(torch.uint8).reshape(-1).cpu().numpy()
-            want = np.ascontiguousarray(o2[rank].data.reshape(-1, order="F")).view(np.uint8)
-            assert got.tobytes() == want.tobytes(), ("inplace", case["name"], rank)
+            src_bytes = A[1].data.view(torch.uint8).reshape(-1).clone()
+            # one-sided methods must notice the aliasing and take the staged schedule
+            for method in (pa.PointToPoint(), pa.PeerPut(), pa.PeerGet(), pa.Alltoallv()):
+                A[1].data.view(torch.uint8).reshape(-1).copy_(src_bytes)
+                pa.transpose_(A[2], A[1], method=method)
+                pa.transpose_(A[3], A[2], method=method)
+                torch.cuda.synchronize()
+                got = A[3].data.view(torch.uint8).reshape(-1).cpu().numpy()
+                want = np.ascontiguousarray(o2[rank].data.reshape(-1, order="F")).view(np.uint8)
+                assert got.tobytes() == want.tobytes(), ("inplace", case["name"], rank, method)
     dist.barrier()
     if rank == 0:
         print(f"MP_WORKER_OK mode={mode} world={world} cases={ran} launches={pa.launch_count()}")

@@ -73,6 +73,30 @@ def test_pack_subbox_to_contiguous(elsize):
              math.prod(parent), math.prod(box) + 7, src_off=11 + 21 * 17 * 3, dst_off=3)
 
 
+def test_bulk_copy_pipeline_rows():
+    """k_rows_bulk (TMA bulk copies through a shared-memory ring) must move the
+    same bytes as k_rows: short runs, long runs, partial chunks, few and many CTAs."""
+    from pencilarrays_b200._lib import lib, check
+    check(lib.pa_set_tunable(b"bulk_rows", 1))
+    try:
+        for ctas in (0, 1, 7, 148):
+            check(lib.pa_set_tunable(b"box_copy_ctas", ctas))
+            run_case([1 << 20], [1], [1], 16, 1 << 20, 1 << 20)                   # 16 MiB, 1-d
+            run_case([1000], [1], [1], 16, 1000, 1000)                            # 16000 B: < one chunk
+            run_case([2049], [1], [1], 16, 2049, 2049)                            # 2 chunks + 16 B
+            parent, box = (64, 24, 32), (32, 24, 32)                              # 512-B runs
+            run_case(list(box), col_major_strides(parent), col_major_strides(box), 16,
+                     math.prod(parent), math.prod(box) + 8, src_off=32, dst_off=8)
+            parent, box = (4096, 6, 5), (2050, 6, 3)                              # 32800-B runs: 3 chunks/row
+            desc = run_case(list(box), col_major_strides(parent), col_major_strides(parent), 16,
+                            math.prod(parent), math.prod(parent), src_off=5, dst_off=4096 * 6 + 7)
+            assert desc.kernel_class == KC_ROWS
+            run_case([256, 37], [1, 300], [1, 256], 4, 300 * 37, 256 * 37)        # f32, 1 KiB runs
+    finally:
+        check(lib.pa_set_tunable(b"bulk_rows", 0))
+        check(lib.pa_set_tunable(b"box_copy_ctas", 0))
+
+
 @pytest.mark.parametrize("elsize", [4, 8, 16])
 @pytest.mark.parametrize("perm", [(1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0), (0, 2, 1)])
 def test_unpack_contiguous_to_permuted_subbox(elsize, perm):

@@ -153,6 +153,16 @@ CASES = [
                 ((2, 3), None)]),
     dict(name="two_ranks_slab", grid=(2,), dims=(20, 16, 4), extra=(), it=4,
          chain=[((1,), None), ((2,), (2, 3, 1)), ((2,), (3, 2, 1)), ((3,), None)]),
+    # BASELINE configs[4] in small: Float32, perms None -> (2,3,1) -> (3,1,2), grids (2,2) and (4,2)
+    dict(name="cfg5_small_2x2", grid=(2, 2), dims=(32, 16, 24), extra=(), it=4,
+         chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 1, 2)), ((1, 3), (2, 3, 1)),
+                ((2, 3), None)]),
+    dict(name="cfg5_small_4x2", grid=(4, 2), dims=(32, 16, 24), extra=(), it=4,
+         chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 1, 2))]),
+    # BASELINE configs[3] in small: ComplexF64 on the (4,2) grid, both schedules
+    dict(name="cfg4_small_4x2", grid=(4, 2), dims=(16, 32, 16), extra=(), it=16,
+         chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1)), ((1, 3), (2, 1, 3)),
+                ((2, 3), None)]),
     # 2-byte elements, extra dim, 4-D data
     dict(name="u16_4d", grid=(2, 2), dims=(6, 5, 4, 7), extra=(2,), it=2,
          chain=[((3, 4), None), ((1, 4), (4, 3, 2, 1)), ((1, 2), (3, 4, 1, 2))]),
