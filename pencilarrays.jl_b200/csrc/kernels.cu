@@ -419,11 +419,13 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
 
   if (b.klass == KC_ROWS && g_tun.bulk_rows && std::min(b.stride_align, pal) == 16) {
     // TMA bulk-copy pipeline (tunable "bulk_rows")
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
       cudaFuncSetAttribute(k_rows_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            BULK_STAGES * BULK_CHUNK);
-      attr_set = true;
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     const long long run = X.e * S;
     const long long chunk = std::min<long long>(BULK_CHUNK, run);
