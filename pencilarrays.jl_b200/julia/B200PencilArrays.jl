@@ -139,6 +139,43 @@ end
 method_code(::PointToPoint) = Cint(0)
 method_code(::Alltoallv) = Cint(1)
 
+# B200 extensions (no reference counterpart): one-sided transposition methods.
+# `PeerPut`: every remote block is stored by ONE kernel straight into the
+# destination rank's `dest` over NVLink; `PeerGet`: pull flavour.  Usage:
+#     t = Transposition(dest, src; method = B200PencilArrays.PeerPut())
+#     B200PencilArrays.register_window!(t)      # collective, once per (dest | src) array
+#     transpose!(t)
+struct PeerPut <: AbstractTransposeMethod end
+struct PeerGet <: AbstractTransposeMethod end
+method_code(::PeerPut) = Cint(2)
+method_code(::PeerGet) = Cint(3)
+
+# Collective over the communicator, like MPI_Win_create: exchanges CUDA IPC
+# handles of the window array (dest for PeerPut, src for PeerGet).
+function register_window!(t::Transposition)
+    plan, H = plan_handle(t)
+    A = t.method isa PeerGet ? parent(t.Ai) : parent(t.Ao)
+    comm = get_comm(t.Pi.topology)
+    handle = zeros(UInt8, 64)
+    off = Ref{Int64}(0)
+    check(ccall((:pa_ipc_export, libpa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int64}), devptr(A), handle, off))
+    handles_all = MPI.Allgather(handle, comm)            # 64 bytes per rank
+    offs_all = MPI.Allgather([off[]], comm)
+    R = t.dim
+    R === nothing && return t
+    line = t.Pi.topology.subcomm_ranks[R]                # world ranks of my grid line (MPITopologies.jl:116)
+    me = MPI.Comm_rank(comm)
+    for (n, r) in enumerate(line)
+        r == me && continue
+        mapped = Ref{Ptr{Cvoid}}()
+        check(ccall((:pa_ipc_import, libpa), Cint, (Ptr{UInt8}, Int64, Ptr{Ptr{Cvoid}}),
+                    view(handles_all, 64r+1:64r+64), offs_all[r + 1], mapped))
+        check(ccall((:pa_plan_set_window, libpa), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                    plan, devptr(A), n, mapped[]))
+    end
+    t
+end
+
 function plan_handle(t::Transposition{T}) where {T}
     H = handles(t.Pi.topology)
     ex = Int64[extra_dims(t.Ai)...]
