@@ -473,13 +473,20 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
   if (b.klass == KC_TRANSPOSE && std::min(b.stride_align, pal) == 16 &&
       (S == 4 || S == 8 || S == 16)) {
     if (vec_used) *vec_used = 16;
+    // destination-run length TBQ*16 B: 512 B by default; 256 B for small blocks
+    // (more, smaller tiles -> shorter tail), tunable "transpose_tbq" overrides
+    int tbq = g_tun.transpose_tbq;
+    if (tbq == 0) tbq = (b.count * S < g_tun.small_block_bytes) ? 16 : 32;
     if (S == 16) {
       p.tiles_x = (unsigned)cdiv(X.e, 32);
-      p.tiles_y = (unsigned)cdiv(Y.e, 32);
+      p.tiles_y = (unsigned)cdiv(Y.e, tbq == 16 ? 16 : tbq == 64 ? 64 : 32);
+      if (tbq == 16) return LAUNCH(k_transpose_vec, 16, 16);
+      if (tbq == 64) return LAUNCH(k_transpose_vec, 16, 64);
       return LAUNCH(k_transpose_vec, 16, 32);
     } else if (S == 8) {
       p.tiles_x = (unsigned)cdiv(X.e, 64);
-      p.tiles_y = (unsigned)cdiv(Y.e, 64);
+      p.tiles_y = (unsigned)cdiv(Y.e, tbq == 16 ? 32 : 64);
+      if (tbq == 16) return LAUNCH(k_transpose_vec, 8, 16);
       return LAUNCH(k_transpose_vec, 8, 32);
     } else {
       p.tiles_x = (unsigned)cdiv(X.e, 128);

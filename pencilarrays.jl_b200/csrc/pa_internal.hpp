@@ -109,7 +109,9 @@ struct Tunables {
   int remote_ctas = -4;   // grid cap of put/get kernels: n > 0 CTAs, n < 0 = |n| per SM, 0 = uncapped
                           // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
-  int bulk_rows = 0;      // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
+  int transpose_tbq = 0;  // 0 = auto; 16 / 32 / 64 = 16-byte items per destination run of a transpose tile
+  long long small_block_bytes = 0;  // blocks below this size use TBQ = 16 (0: never)
+  int bulk_rows = 0;     // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
 };
 extern Tunables g_tun;

@@ -109,7 +109,11 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--tunable", action="append", default=[], help="name=value for pa_set_tunable")
     a = ap.parse_args()
+    for tv in a.tunable:
+        k, v = tv.split("=")
+        check(lib.pa_set_tunable(k.encode(), int(v)))
     rows = []
     X, Y, Z = (2, 3), (1, 3), (1, 2)
     cfgs = [
