@@ -29,6 +29,16 @@ GIB = float(1 << 30)
 PER_GPU = (512, 512, 512)           # ComplexF64 shard per GPU: 2 GiB
 CHAIN = [((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1))]  # x, y, z pencils
 LEGS = ["x->y", "y->z", "z->y", "y->x"]
+# --workload: "cfg4" (default, above) or "cfg5" = BASELINE configs[4]: Float32,
+# 1 GiB per GPU ((1024,512,512) per GPU -> 2048x1024x1024 at N = 8), perms None -> (2,3,1) -> (3,1,2)
+WORKLOADS = {
+    "cfg4": dict(per_gpu=PER_GPU, chain=CHAIN, dtype="complex128", itemsize=16, tname="ComplexF64",
+                 perms="None->(2,1,3)->(3,2,1)", note="2 GiB per GPU; N=8 is BASELINE configs[3]"),
+    "cfg5": dict(per_gpu=(1024, 512, 512),
+                 chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 1, 2))],
+                 dtype="float32", itemsize=4, tname="Float32", perms="None->(2,3,1)->(3,1,2)",
+                 note="1 GiB per GPU; N=8 is BASELINE configs[4]"),
+}
 
 
 def grid_and_dims(n, per_gpu=PER_GPU):
@@ -193,11 +203,11 @@ def run_reference(args):
     }))
 
 
-def workload_name(n):
-    grid, dims = grid_and_dims(n)
-    return (f"x->y->z->y->x transpose! chain, {dims[0]}x{dims[1]}x{dims[2]} ComplexF64, "
-            f"process grid {grid}, perms None->(2,1,3)->(3,2,1) "
-            f"(2 GiB per GPU; N=8 is BASELINE configs[3])")
+def workload_name(n, wl="cfg4"):
+    W = WORKLOADS[wl]
+    grid, dims = grid_and_dims(n, W["per_gpu"])
+    return (f"x->y->z->y->x transpose! chain, {dims[0]}x{dims[1]}x{dims[2]} {W['tname']}, "
+            f"process grid {grid}, perms {W['perms']} ({W['note']})")
 
 
 # ------------------------------------------------------------------------- B200 arm
@@ -216,15 +226,17 @@ def run_b200(args):
     torch.cuda.set_device(local)
     comm = pa.comm_world() if n > 1 else pa.COMM_SELF
     rank = comm.rank
-    grid, dims = grid_and_dims(n)
+    W = WORKLOADS[args.workload]
+    chain_cfg, isz = W["chain"], W["itemsize"]
+    grid, dims = grid_and_dims(n, W["per_gpu"])
     topo = pa.MPITopology(comm, grid)
-    px = pa.Pencil(topo, dims, CHAIN[0][0])
-    py = pa.Pencil(px, decomp_dims=CHAIN[1][0], permute=pa.Permutation(*CHAIN[1][1]))
-    pz = pa.Pencil(py, decomp_dims=CHAIN[2][0], permute=pa.Permutation(*CHAIN[2][1]))
-    dt = torch.complex128
+    px = pa.Pencil(topo, dims, chain_cfg[0][0])
+    py = pa.Pencil(px, decomp_dims=chain_cfg[1][0], permute=pa.Permutation(*chain_cfg[1][1]))
+    pz = pa.Pencil(py, decomp_dims=chain_cfg[2][0], permute=pa.Permutation(*chain_cfg[2][1]))
+    dt = getattr(torch, W["dtype"])
     ux, uy, uz = (pa.PencilArray.undef(dt, p) for p in (px, py, pz))
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
-    ux.data.view(torch.float64).normal_(generator=gen)
+    ux.data.view(torch.float64 if isz == 16 else dt).normal_(generator=gen)
     orig = ux.data.clone()
     methods = {"alltoallv": pa.Alltoallv(), "pointtopoint": pa.PointToPoint(),
                "peerput": pa.PeerPut(), "peerget": pa.PeerGet()}
@@ -299,12 +311,12 @@ def run_b200(args):
             leg_ms[i] += legs[k][i].elapsed_time(legs[k][i + 1]) / args.steps
     leg_ms = [max_over_ranks(x) for x in leg_ms]
     ok = bool(torch.equal(ux.data.view(torch.uint8), orig.view(torch.uint8)))
-    gbytes = math.prod(dims) * 16
+    gbytes = math.prod(dims) * isz
     value = 4 * gbytes / GIB / (ms * 1e-3)
 
     # ---- per-kernel roofline (kernels timed alone on the current stream) -------
     peak, peak_src = measured_peak()
-    shard = ux.data.numel() * 16
+    shard = ux.data.numel() * isz
     kern = {}
     if n == 1:
         # each leg IS one launch of the fused permuting kernel (K3); live numbers from the timed steps
@@ -339,7 +351,7 @@ def run_b200(args):
                 b.record()
                 torch.cuda.synchronize()
                 m = a.elapsed_time(b) / 5
-                nb = 2 * (info.length_in if op == 0 else info.length_out) * 16
+                nb = 2 * (info.length_in if op == 0 else info.length_out) * isz
                 kern[f"{label} {name} (all {info.nproc} blocks)"] = {
                     "ms": round(m, 4), "alg_bytes": nb, "GBps": round(nb / m / 1e6, 1)}
         chain()  # restore a consistent state after the isolated kernels scribbled on uy/uz
@@ -371,7 +383,7 @@ def run_b200(args):
     b.record()
     barrier()
     e2e_ms = max_over_ranks(a.elapsed_time(b)) / e2e_steps
-    e2e_ok = bool(torch.equal(hout.view(torch.float64), hin.view(torch.float64)))
+    e2e_ok = bool(torch.equal(hout.view(torch.uint8), hin.view(torch.uint8)))
     e2e_val = 4 * gbytes / GIB / (e2e_ms * 1e-3)
 
     # ---- exchange timing (N > 1): library CUDA-event sections, sequential phases ----
@@ -404,8 +416,8 @@ def run_b200(args):
             "metric": "transpose_GiB_per_s", "value": round(value, 2), "unit": "GiB/s", "n_gpus": n,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "c128 (bytes; pure data movement)", "data": "synthetic",
-            "config": {"workload": workload_name(n), "method": repr(method), "overlap": overlap,
+            "dtype": ("c128" if isz == 16 else "f32") + " (bytes; pure data movement)", "data": "synthetic",
+            "config": {"workload": workload_name(n, args.workload), "method": repr(method), "overlap": overlap,
                        "l2": "inputs (2 GiB per GPU) far larger than the 126 MB L2; no flush needed",
                        "round_trip_bit_exact": ok, "leg_ms": dict(zip(LEGS, [round(x, 4) for x in leg_ms]))},
             "gpu_launches": int(launches),
@@ -476,6 +488,7 @@ def main():
     ap.add_argument("--method", default="auto",
                     choices=["auto", "pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--nccl-fences", action="store_true",
                     help="one-sided methods: fence with NCCL groups instead of NVLink flags")
     ap.add_argument("--remote-ctas", type=int, default=None,

@@ -110,7 +110,9 @@ struct Tunables {
                           // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
   int transpose_tbq = 0;  // 0 = auto; 16 / 32 / 64 = 16-byte items per destination run of a transpose tile
-  long long small_block_bytes = 0;  // blocks below this size use TBQ = 16 (0: never)
+  // blocks below this size use TBQ = 16: 256^3 Float64 permutes go from 76 % to 94 % of the HBM
+  // roofline, 1-2 GiB blocks are indifferent (profiles/r1_tile_sweep.txt)
+  long long small_block_bytes = 256ll << 20;
   int bulk_rows = 0;     // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
 };
