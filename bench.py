@@ -56,55 +56,82 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region: the sampler
+    runs from before the warm-up (nvidia-smi needs ~1 s to start) at 10 ms
+    period; rows are time-stamped and only those inside [mark_start, mark_stop]
+    (host clock, bracketing the timed steps) are reported.  If the region is
+    shorter than the sampling allows, the rows within 250 ms of it are used and
+    `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            t = time.time()
+            while not self.rows and time.time() - t < 3.0:  # wait for the first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()  # exact PID we started
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            c = [x.strip() for x in r.split(",")]
-            if len(c) < 6:
-                continue
-            try:
-                sm.append(float(c[0]))
-                mx.append(float(c[1]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, c[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                c = [x.strip() for x in r.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            return sm, mx, reasons
+
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [r for r in self.rows if t0 - 0.25 <= r[0] <= t1 + 0.25]
+            window = "timed region +-250 ms (region shorter than the sampling period)"
+        sm, mx, reasons = parse(inside)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "region_ms": round((t1 - t0) * 1e3, 1),
+                "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------- reference arm
@@ -145,7 +172,7 @@ def run_reference(args):
     sample = tuple(s // 2 for s in PER_GPU)
     grid, dims = grid_and_dims(n, sample)
     nranks = math.prod(grid)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     dtype = np.complex128
     steps_cfg = CHAIN + [CHAIN[1], CHAIN[0]]
     cts = [c_oracle.CTranspose(grid, dims, steps_cfg[i][0], steps_cfg[i][1], steps_cfg[i + 1][0],
@@ -287,13 +314,14 @@ def run_b200(args):
                 evs[i + 1].record()
 
     # ---- device-resident timing -------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         chain()
     leg_ms = [0.0] * 4
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.mark_start()
     n0 = pa.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     legs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(args.steps)]
@@ -303,6 +331,7 @@ def run_b200(args):
         chain(legs[k])
     e1.record()
     barrier()
+    sampler.mark_stop()
     launches = pa.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
@@ -450,7 +479,7 @@ def cpu_baseline():
     from oracle import c_oracle
     dims = (256, 256, 256)
     grid = (1, 1)
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) or 1
     cfg = CHAIN + [CHAIN[1], CHAIN[0]]
     cts = [c_oracle.CTranspose(grid, dims, cfg[i][0], cfg[i][1], cfg[i + 1][0], cfg[i + 1][1], (),
                                np.complex128) for i in range(4)]
@@ -482,7 +511,7 @@ def cpu_baseline():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--method", default="auto",
