@@ -293,6 +293,8 @@ def run_b200(args):
         pa.check(pa.lib.pa_set_tunable(b"remote_ctas", args.remote_ctas))
     if args.nccl_fences:
         pa.check(pa.lib.pa_set_tunable(b"nccl_fences", 1))
+    if args.nccl_register:
+        pa.check(pa.lib.pa_set_tunable(b"nccl_register", 1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -392,6 +394,36 @@ def run_b200(args):
     except Exception:
         pass
 
+    # ---- BASELINE configs[1] beside it (N == 1): 256^3 Float64, 1 GPU, pack/unpack kernel only ----
+    cfg1 = None
+    if n == 1 and args.workload == "cfg4":
+        cfg1 = {}
+        topo1 = pa.MPITopology(pa.COMM_SELF, (1, 1))
+        q1 = pa.Pencil(topo1, (256, 256, 256), (2, 3))
+        a1 = pa.PencilArray.undef(torch.float64, q1)
+        a1.data.normal_()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        for perm in ((2, 1, 3), (2, 3, 1), (3, 2, 1), (3, 1, 2), (1, 3, 2), None):
+            q2 = pa.Pencil(q1, decomp_dims=(1, 3),
+                           permute=pa.NoPermutation() if perm is None else pa.Permutation(*perm))
+            b1 = pa.PencilArray.undef(torch.float64, q2)
+            t1 = pa.Transposition(b1, a1)
+            tot = 0.0
+            for it in range(8):
+                flush.zero_()  # evict src/dst from L2 between launches
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                pa.transpose_(t1)
+                e_.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    tot += s_.elapsed_time(e_) / 5
+            nb = 2 * a1.data.numel() * 8
+            cfg1[f"x->y perm {perm}"] = {"ms": round(tot, 4), "GBps": round(nb / tot / 1e6, 1),
+                                         "frac_of_hbm_peak": round(nb / tot / 1e6 / peak, 3)}
+        cfg1["note"] = ("256^3 Float64 x->y on 1 GPU = one fused K3 launch per transpose!; L2 flushed "
+                        "(256 MiB memset) before every timed launch; 2*s*n algorithmic bytes")
+
     # ---- end to end: host buffers in, host buffers out -------------------------
     hin = torch.empty(ux.data.shape, dtype=dt).pin_memory()
     hin.copy_(orig)
@@ -464,6 +496,7 @@ def run_b200(args):
                 "timing": ("CUDA events on the launching stream inside the timed steps" if n == 1 else
                            "CUDA events, kernels launched alone on the current stream in this run")},
             "kernels": kern,
+            "configs1_256cubed_f64": cfg1,
             "sections": sections,
             "cpu_baseline": cpu,
         }
@@ -518,6 +551,8 @@ def main():
                     choices=["auto", "pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--nccl-register", action="store_true",
+                    help="staged methods: arenas from ncclMemAlloc, registered with the communicator")
     ap.add_argument("--nccl-fences", action="store_true",
                     help="one-sided methods: fence with NCCL groups instead of NVLink flags")
     ap.add_argument("--remote-ctas", type=int, default=None,

@@ -54,6 +54,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   else if (!strcmp(name, "box_copy_ctas")) g_tun.box_copy_ctas = (int)value;
   else if (!strcmp(name, "nccl_fences")) g_tun.nccl_fences = (int)value;
   else if (!strcmp(name, "bulk_rows")) g_tun.bulk_rows = (int)value;
+  else if (!strcmp(name, "nccl_register")) g_tun.nccl_register = (int)value;
   else if (!strcmp(name, "transpose_tbq")) g_tun.transpose_tbq = (int)value;
   else if (!strcmp(name, "small_block_bytes")) g_tun.small_block_bytes = value;
   else {

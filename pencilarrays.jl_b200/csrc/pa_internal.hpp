@@ -42,6 +42,15 @@ struct Buffers {
   void* recv = nullptr;
   i64 recv_cap = 0;
   void* comm_done_event = nullptr;  // cudaEvent_t of the last exchange using them
+  // NCCL user-buffer registration (tunable "nccl_register"): arenas come from
+  // ncclMemAlloc and are registered with the communicator so that ncclSend /
+  // ncclRecv can go zero-copy over NVLink instead of through NCCL's staging FIFO
+  bool send_nccl = false, recv_nccl = false;  // allocated with ncclMemAlloc
+  void* reg_comm = nullptr;                   // ncclComm_t the arenas are registered with
+  void* reg_send = nullptr;                   // registration handles
+  void* reg_recv = nullptr;
+  void* reg_send_ptr = nullptr;               // the pointers that were registered
+  void* reg_recv_ptr = nullptr;
   ~Buffers();
   pa_status reserve(i64 send_bytes, i64 recv_bytes);
 };
@@ -114,6 +123,7 @@ struct Tunables {
   // roofline, 1-2 GiB blocks are indifferent (profiles/r1_tile_sweep.txt)
   long long small_block_bytes = 256ll << 20;
   int bulk_rows = 0;     // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
+  int nccl_register = 0;  // 1: staging arenas from ncclMemAlloc + ncclCommRegister (zero-copy NCCL p2p)
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
 };
 extern Tunables g_tun;

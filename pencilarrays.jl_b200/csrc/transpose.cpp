@@ -20,6 +20,7 @@
 #include <nccl.h>
 
 #include <mutex>
+#include <set>
 
 #include "pa_internal.hpp"
 
@@ -119,6 +120,10 @@ struct NcclApi {
   decltype(&ncclGroupEnd) GroupEnd = nullptr;
   decltype(&ncclGetErrorString) GetErrorString = nullptr;
   decltype(&ncclGetVersion) GetVersion = nullptr;
+  decltype(&ncclMemAlloc) MemAlloc = nullptr;        // optional (user-buffer registration)
+  decltype(&ncclMemFree) MemFree = nullptr;
+  decltype(&ncclCommRegister) CommRegister = nullptr;
+  decltype(&ncclCommDeregister) CommDeregister = nullptr;
   bool ok = false;
 };
 
@@ -142,6 +147,10 @@ static NcclApi& nccl() {
     LOAD(GroupEnd);
     LOAD(GetErrorString);
     LOAD(GetVersion);
+    LOAD(MemAlloc);
+    LOAD(MemFree);
+    LOAD(CommRegister);
+    LOAD(CommDeregister);
 #undef LOAD
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv &&
              api.GroupStart && api.GroupEnd && api.GetErrorString;
@@ -215,6 +224,9 @@ pa_status comm_unique_id(void* id128) {
   return PA_OK;
 }
 
+static std::mutex g_live_mu;
+static std::set<void*> g_live_comms;  // communicators that may still hold registrations
+
 pa_status comm_init(const void* id128, int nranks, int rank, Comm** out) {
   if (!nccl().ok) {
     set_error("libnccl.so.2 could not be loaded");
@@ -231,12 +243,20 @@ pa_status comm_init(const void* id128, int nranks, int rank, Comm** out) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof id);
   NC(nccl().CommInitRank(&c->comm, nranks, id, rank));
+  {
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    g_live_comms.insert((void*)c->comm);
+  }
   *out = c.release();
   return PA_OK;
 }
 
 void comm_destroy(Comm* c) {
   if (!c) return;
+  {
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    g_live_comms.erase((void*)c->comm);
+  }
   if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
   if (c->flags) cudaFree(c->flags);
   if (c->fence_err) cudaFreeHost(c->fence_err);
@@ -275,29 +295,74 @@ pa_status comm_flags_import(Comm* c, int rank, const void* handle64, i64 offset)
 }
 
 // ---- staging arenas ----------------------------------------------------------
+static void buffers_deregister(Buffers& b) {
+  if (!b.reg_comm) return;
+  bool live;
+  {
+    std::lock_guard<std::mutex> lock(g_live_mu);
+    live = g_live_comms.count(b.reg_comm) != 0;
+  }
+  if (live && nccl().CommDeregister) {
+    if (b.reg_send) nccl().CommDeregister((ncclComm_t)b.reg_comm, b.reg_send);
+    if (b.reg_recv) nccl().CommDeregister((ncclComm_t)b.reg_comm, b.reg_recv);
+  }
+  b.reg_comm = b.reg_send = b.reg_recv = b.reg_send_ptr = b.reg_recv_ptr = nullptr;
+}
+
+static void free_arena(void* p, bool from_nccl) {
+  if (!p) return;
+  if (from_nccl && nccl().MemFree) nccl().MemFree(p);
+  else cudaFree(p);
+}
+
 Buffers::~Buffers() {
-  if (send) cudaFree(send);
-  if (recv) cudaFree(recv);
+  buffers_deregister(*this);
+  free_arena(send, send_nccl);
+  free_arena(recv, recv_nccl);
   if (comm_done_event) cudaEventDestroy((cudaEvent_t)comm_done_event);
 }
 
 // grow-only, like resize! on the pencil's UInt8 vectors (Transpositions.jl:313-317)
 pa_status Buffers::reserve(i64 send_bytes, i64 recv_bytes) {
-  auto grow = [](void*& p, i64& cap, i64 need) -> pa_status {
+  auto grow = [this](void*& p, i64& cap, bool& from_nccl, i64 need) -> pa_status {
     if (need <= cap) return PA_OK;
     // a previous exchange may still be reading/writing the old arena
     CU(cudaDeviceSynchronize());
-    if (p) CU(cudaFree(p));
+    buffers_deregister(*this);
+    free_arena(p, from_nccl);
     p = nullptr;
     cap = 0;
     i64 n = (need + 255) / 256 * 256;
-    CU(cudaMalloc(&p, (size_t)n));
+    from_nccl = false;
+    if (g_tun.nccl_register && nccl().ok && nccl().MemAlloc && nccl().MemFree &&
+        nccl().MemAlloc(&p, (size_t)n) == ncclSuccess && p) {
+      from_nccl = true;
+    } else {
+      p = nullptr;
+      CU(cudaMalloc(&p, (size_t)n));
+    }
     cap = n;
     return PA_OK;
   };
-  pa_status s = grow(send, send_cap, send_bytes);
+  pa_status s = grow(send, send_cap, send_nccl, send_bytes);
   if (s != PA_OK) return s;
-  return grow(recv, recv_cap, recv_bytes);
+  return grow(recv, recv_cap, recv_nccl, recv_bytes);
+}
+
+// register the arenas with `comm` (no-op unless tunable nccl_register and ncclMemAlloc'ed arenas)
+static void buffers_register(Buffers& b, ncclComm_t comm) {
+  if (!g_tun.nccl_register || !nccl().CommRegister) return;
+  if (b.reg_comm == (void*)comm && b.reg_send_ptr == b.send && b.reg_recv_ptr == b.recv) return;
+  buffers_deregister(b);
+  b.reg_comm = (void*)comm;
+  if (b.send && b.send_nccl &&
+      nccl().CommRegister(comm, b.send, (size_t)b.send_cap, &b.reg_send) != ncclSuccess)
+    b.reg_send = nullptr;
+  if (b.recv && b.recv_nccl &&
+      nccl().CommRegister(comm, b.recv, (size_t)b.recv_cap, &b.reg_recv) != ncclSuccess)
+    b.reg_recv = nullptr;
+  b.reg_send_ptr = b.send;
+  b.reg_recv_ptr = b.recv;
 }
 
 // ---- per-plan stream/event state --------------------------------------------
@@ -470,6 +535,7 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
     rc = B.reserve(need_send, need_recv);
     if (rc != PA_OK) return rc;
   }
+  if (comm && nproc > 1) buffers_register(B, comm->comm);
   char* sbuf = (char*)B.send;
   char* rbuf = (char*)B.recv;
   const Peer& self = P->peers[me];
