@@ -293,8 +293,8 @@ def run_b200(args):
         pa.check(pa.lib.pa_set_tunable(b"remote_ctas", args.remote_ctas))
     if args.nccl_fences:
         pa.check(pa.lib.pa_set_tunable(b"nccl_fences", 1))
-    if args.nccl_register:
-        pa.check(pa.lib.pa_set_tunable(b"nccl_register", 1))
+    if args.no_nccl_register:
+        pa.check(pa.lib.pa_set_tunable(b"nccl_register", 0))
 
     def barrier():
         torch.cuda.synchronize()
@@ -551,8 +551,8 @@ def main():
                     choices=["auto", "pointtopoint", "alltoallv", "peerput", "peerget"])
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
-    ap.add_argument("--nccl-register", action="store_true",
-                    help="staged methods: arenas from ncclMemAlloc, registered with the communicator")
+    ap.add_argument("--no-nccl-register", action="store_true",
+                    help="staged methods: plain cudaMalloc arenas, no NCCL user-buffer registration")
     ap.add_argument("--nccl-fences", action="store_true",
                     help="one-sided methods: fence with NCCL groups instead of NVLink flags")
     ap.add_argument("--remote-ctas", type=int, default=None,

@@ -123,7 +123,8 @@ struct Tunables {
   // roofline, 1-2 GiB blocks are indifferent (profiles/r1_tile_sweep.txt)
   long long small_block_bytes = 256ll << 20;
   int bulk_rows = 0;     // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
-  int nccl_register = 0;  // 1: staging arenas from ncclMemAlloc + ncclCommRegister (zero-copy NCCL p2p)
+  int nccl_register = 1;  // staging arenas from ncclMemAlloc + ncclCommRegister (registered NCCL p2p:
+                          // exchange 637 -> 673 GB/s at N=2); falls back to cudaMalloc when unavailable
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
 };
 extern Tunables g_tun;
