@@ -163,7 +163,11 @@ function register_window!(t::Transposition)
     offs_all = MPI.Allgather([off[]], comm)
     R = t.dim
     R === nothing && return t
-    line = t.Pi.topology.subcomm_ranks[R]                # world ranks of my grid line (MPITopologies.jl:116)
+    # ranks (in `comm`) of my grid line along R: topology.ranks maps Cartesian
+    # coordinates to ranks (MPITopologies.jl:84-86,208-226); get_remote_indices (:539-549)
+    topo = t.Pi.topology
+    coords = topo.coords_local
+    line = [topo.ranks[ntuple(i -> i == R ? n : coords[i], length(coords))...] for n in 1:size(topo)[R]]
     me = MPI.Comm_rank(comm)
     for (n, r) in enumerate(line)
         r == me && continue
