@@ -345,6 +345,33 @@ def run_b200(args):
     gbytes = math.prod(dims) * isz
     value = 4 * gbytes / GIB / (ms * 1e-3)
 
+    # ---- placement check at full size (not timed): a round trip alone would also pass for a
+    # wrong-but-invertible shuffle, so every rank fills x with a function of the GLOBAL logical
+    # index and checks that after x->y and y->z each element sits where the pencil geometry says:
+    # parent(u)[perm * I] == global[I + offset]  (arrays.jl:327-337)
+    def pattern(pen):
+        rl = pa.range_local(pen)
+        ax = [torch.arange(r.start - 1, r.stop - 1, device="cuda", dtype=torch.float64) for r in rl]
+        lin = ax[0][:, None, None] + dims[0] * (ax[1][None, :, None] + dims[1] * ax[2][None, None, :])
+        if isz == 16:
+            return torch.complex(lin, -lin)
+        return torch.remainder(lin, 16777216.0).to(dt)  # exact in Float32
+
+    good, perr = 0, None
+    try:
+        ux.logical().copy_(pattern(px))
+        pa.transpose_(ts[0], waitall=True, overlap=overlap)
+        pa.transpose_(ts[1], waitall=True, overlap=overlap)
+        good = int(bool(torch.equal(uy.logical(), pattern(py))) and
+                   bool(torch.equal(uz.logical(), pattern(pz))))
+    except Exception as e:  # never lose the bench line over the checker
+        perr = f"checker error: {type(e).__name__}: {e}"[:200]
+    flag = torch.tensor([good], device="cuda")
+    if n > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank takes part, whatever happened above
+    placement = perr if perr else bool(flag.item())
+    torch.cuda.empty_cache()
+
     # ---- per-kernel roofline (kernels timed alone on the current stream) -------
     peak, peak_src = measured_peak()
     shard = ux.data.numel() * isz
@@ -509,7 +536,7 @@ def run_b200(args):
             "dtype": ("c128" if isz == 16 else "f32") + " (bytes; pure data movement)", "data": "synthetic",
             "config": {"workload": workload_name(n, args.workload), "method": repr(method), "overlap": overlap,
                        "l2": "inputs (2 GiB per GPU) far larger than the 126 MB L2; no flush needed",
-                       "round_trip_bit_exact": ok, "leg_ms": dict(zip(LEGS, [round(x, 4) for x in leg_ms]))},
+                       "round_trip_bit_exact": ok, "placement_exact_full_size": placement, "leg_ms": dict(zip(LEGS, [round(x, 4) for x in leg_ms]))},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 2), "unit": "GiB/s", "ms_per_step": round(e2e_ms, 3),
