@@ -107,6 +107,49 @@ def test_put_kernels_emulated_ranks(case):
         cur_o = nxt_o
 
 
+@pytest.mark.parametrize("itemsize", [24, 12, 48])
+def test_non_power_of_two_element_sizes_gpu(itemsize):
+    """24-byte (SVector{3,Float64}-like), 12-byte and 48-byte elements through the
+    kernels: staged (pack/unpack), fused self block, put and get."""
+    edt = np.dtype((np.void, itemsize))
+    case = dict(name="odd_elsize", grid=(2, 2), dims=(6, 7, 5), extra=(2,), it=itemsize,
+                chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 2, 1)), ((1, 2), (1, 3, 2))])
+    ranks, steps = build_chain(case)
+    rng = np.random.default_rng(7)
+    n_glob = math.prod(case["dims"]) * math.prod(case["extra"])
+    gbytes = rng.integers(0, 256, size=(n_glob, itemsize), dtype=np.uint8)
+    g = gbytes.reshape(case["dims"] + case["extra"] + (itemsize,), order="F")
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], case["extra"], edt)
+    from gpu_util import stream_ptr
+    for k in range(1, len(steps)):
+        nxt_o = [O.OArray.undef(edt, po, *case["extra"]) for (_, po) in steps[k]]
+        O.transpose_all(nxt_o, cur_o)
+        plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], case["extra"], itemsize, pa.PeerPut())
+                 for r in range(len(ranks))]
+        cur = [dev_bytes(a.data.reshape(-1, order="F")) for a in cur_o]
+        wants = [np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8) for a in nxt_o]
+        for mode in ("staged", "fused", "put", "get"):
+            nxt = [torch.full((max(1, w.size),), 0x11, dtype=torch.uint8, device="cuda") for w in wants]
+            if mode in ("staged", "fused") or plans[0].info.dim == 0:
+                emulate_transpose_gpu(plans, cur, nxt, fused_self=(mode == "fused"))
+            else:
+                st = stream_ptr()
+                for r, pl in enumerate(plans):
+                    check(lib.pa_copy_self(pl.h, ptr(cur[r]), ptr(nxt[r]), st))
+                    for p in range(1, pl.info.nproc + 1):
+                        peer = pl.peer(p)
+                        if peer.is_self:
+                            continue
+                        if mode == "put":
+                            check(lib.pa_put(pl.h, p, ptr(cur[r]), ptr(nxt[peer.world_rank]), st))
+                        else:
+                            check(lib.pa_get(pl.h, p, ptr(cur[peer.world_rank]), ptr(nxt[r]), st))
+            torch.cuda.synchronize()
+            for r, w in enumerate(wants):
+                assert host_bytes(nxt[r])[:w.size].tobytes() == w.tobytes(), (itemsize, k, r, mode)
+        cur_o = nxt_o
+
+
 # ---------------------------------------------------------------- public API, one rank
 def _fill(u: pa.PencilArray, seed):
     raw = torch.randint(0, 256, (u.data.numel() * u.elsize,), dtype=torch.uint8, device="cuda",

@@ -135,3 +135,32 @@ def test_counts_are_symmetric():
                     assert back.send_count == peer.recv_count
                 assert tot_s == pl.info.send_bytes
                 assert tot_r + pl.info.length_self * case["it"] == pl.info.recv_bytes
+
+
+@pytest.mark.parametrize("itemsize", [24, 12, 48])
+def test_non_power_of_two_element_sizes(itemsize):
+    """Elements such as SVector{3,Float64} (24 B) or 3 x Float32 (12 B) move as
+    several power-of-two words: the planner adds an innermost word dimension."""
+    word = max(w for w in (1, 2, 4, 8, 16) if itemsize % w == 0)  # the planner's word size
+    wdt = np.dtype((np.void, word))
+    edt = np.dtype((np.void, itemsize))
+    case = dict(name="odd_elsize", grid=(2, 2), dims=(6, 7, 5), extra=(2,), it=itemsize,
+                chain=[((2, 3), None), ((1, 3), (2, 3, 1)), ((1, 2), (3, 2, 1)), ((1, 2), (1, 3, 2))])
+    ranks, steps = build_chain(case)
+    rng = np.random.default_rng(7)
+    n_glob = math.prod(case["dims"]) * math.prod(case["extra"])
+    gbytes = rng.integers(0, 256, size=(n_glob, itemsize), dtype=np.uint8)
+    g = gbytes.reshape(case["dims"] + case["extra"] + (itemsize,), order="F")
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], case["extra"], edt)
+    for k in range(1, len(steps)):
+        nxt_o = [O.OArray.undef(edt, po, *case["extra"]) for (_, po) in steps[k]]
+        O.transpose_all(nxt_o, cur_o)
+        plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], case["extra"], itemsize, pa.PointToPoint())
+                 for r in range(len(ranks))]
+        cur = [np.ascontiguousarray(a.data.reshape(-1, order="F")).view(wdt) for a in cur_o]
+        nxt = [np.zeros(max(1, a.data.size * itemsize // word), dtype=wdt) for a in nxt_o]
+        emulate_transpose_with_descriptors(plans, cur, nxt, wdt)
+        for r, a in enumerate(nxt_o):
+            want = np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8)
+            assert nxt[r].view(np.uint8)[:want.size].tobytes() == want.tobytes(), (k, r)
+        cur_o = nxt_o
