@@ -73,6 +73,31 @@ def test_pack_subbox_to_contiguous(elsize):
              math.prod(parent), math.prod(box) + 7, src_off=11 + 21 * 17 * 3, dst_off=3)
 
 
+@pytest.mark.parametrize("ctas", [1, 5, -1])
+def test_capped_grid_flavours(ctas):
+    """The tile-striding (LOOP=true) flavour of every kernel -- what the NVLink
+    put/get paths launch -- must move the same bytes as the one-tile-per-CTA one."""
+    from pencilarrays_b200._lib import lib, check
+    check(lib.pa_set_tunable(b"box_copy_ctas", ctas))
+    try:
+        for elsize in (1, 4, 8, 16):
+            for dims in ((70, 33, 9), (128, 64, 12)):
+                n = math.prod(dims)
+                ss = col_major_strides(dims)
+                for perm in ((0, 1, 2), (1, 0, 2), (2, 0, 1)):
+                    dcol = col_major_strides([dims[p] for p in perm])
+                    ds = [0, 0, 0]
+                    for i, p in enumerate(perm):
+                        ds[p] = dcol[i]
+                    run_case(list(dims), ss, ds, elsize, n, n, seed=elsize + sum(perm))
+        # narrow row copies (odd sizes -> 8/4/2/1-byte vectors) and a long 1-d run
+        run_case([21, 17, 13], col_major_strides((23, 17, 13)), col_major_strides((21, 17, 13)), 8,
+                 23 * 17 * 13, 21 * 17 * 13)
+        run_case([300001], [1], [1], 2, 300001, 300001)
+    finally:
+        check(lib.pa_set_tunable(b"box_copy_ctas", 0))
+
+
 def test_bulk_copy_pipeline_rows():
     """k_rows_bulk (TMA bulk copies through a shared-memory ring) must move the
     same bytes as k_rows: short runs, long runs, partial chunks, few and many CTAs."""
