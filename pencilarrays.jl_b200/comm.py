@@ -47,6 +47,7 @@ class Comm:
 
 
 COMM_SELF = Comm(0, 1)
+_WORLD = None
 
 
 def comm_world(init_nccl: bool | None = None) -> Comm:
@@ -59,6 +60,9 @@ def comm_world(init_nccl: bool | None = None) -> Comm:
     import torch
     import torch.distributed as dist
 
+    global _WORLD
+    if _WORLD is not None and (init_nccl is None or bool(init_nccl) == (_WORLD.handle is not None)):
+        return _WORLD  # MPI.COMM_WORLD is a singleton: do not build a second NCCL communicator
     if not dist.is_initialized():
         if "RANK" not in os.environ:
             return COMM_SELF
@@ -99,4 +103,5 @@ def comm_world(init_nccl: bool | None = None) -> Comm:
         dist.all_gather_object(oks, ok)
         if not all(oks):  # all ranks must fence the same way
             check(lib.pa_set_tunable(b"nccl_fences", 1))
-    return Comm(rank, size, handle=handle)
+    _WORLD = Comm(rank, size, handle=handle)
+    return _WORLD
