@@ -90,6 +90,28 @@ def _run(case, on_gpu):
         cur_o = nxt_o
 
 
+@pytest.mark.parametrize("case", RANDOM_CASES[:25], ids=[c["name"] for c in RANDOM_CASES[:25]])
+def test_random_geometry_api_vs_oracle(case):
+    """`range_local`, `range_remote`, `size_local`, `to_local` of the host mirror
+    (computed by libpa_b200) against the oracle's axes for every rank."""
+    import itertools as it_
+    ranks, steps = build_chain(case)
+    for pens in steps:
+        for r, (p, op) in enumerate(pens):
+            assert pa.range_local(p) == op.axes_local
+            assert pa.range_local(p, pa.MemoryOrder()) == op.axes_local_perm
+            assert pa.size_local(p, pa.MemoryOrder()) == op.size_local(True)
+            assert pa.size_global(p) == op.size_global
+            assert p.topology.coords_local == op.topology.coords_local
+            for coords in it_.product(*[range(1, d + 1) for d in case["grid"]]):
+                assert pa.range_remote(p, coords) == op.axes_all[coords]
+                assert p.topology.rank_of(coords) == op.topology.rank_of(coords)
+            probe = tuple(range(rg.start, min(rg.stop, rg.start + 2)) for rg in op.axes_local)
+            for mem in (False, True):
+                order = pa.MemoryOrder() if mem else pa.LogicalOrder()
+                assert pa.to_local(p, probe, order) == op.to_local(probe, memory_order=mem)
+
+
 @pytest.mark.parametrize("case", RANDOM_CASES, ids=[c["name"] for c in RANDOM_CASES])
 def test_random_planner_vs_oracle(case):
     _run(case, on_gpu=False)
