@@ -479,9 +479,9 @@ pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* str
     if (tbq == 0) tbq = (b.count * S < g_tun.small_block_bytes) ? 16 : 32;
     if (S == 16) {
       p.tiles_x = (unsigned)cdiv(X.e, 32);
-      p.tiles_y = (unsigned)cdiv(Y.e, tbq == 16 ? 16 : tbq == 64 ? 64 : 32);
+      // (a 1-KiB-run tile, TBQ = 64, measured 14 % slower: profiles/r1_analysis.md; not kept)
+      p.tiles_y = (unsigned)cdiv(Y.e, tbq == 16 ? 16 : 32);
       if (tbq == 16) return LAUNCH(k_transpose_vec, 16, 16);
-      if (tbq == 64) return LAUNCH(k_transpose_vec, 16, 64);
       return LAUNCH(k_transpose_vec, 16, 32);
     } else if (S == 8) {
       p.tiles_x = (unsigned)cdiv(X.e, 64);

@@ -118,7 +118,7 @@ struct Tunables {
   int remote_ctas = -4;   // grid cap of put/get kernels: n > 0 CTAs, n < 0 = |n| per SM, 0 = uncapped
                           // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
-  int transpose_tbq = 0;  // 0 = auto; 16 / 32 / 64 = 16-byte items per destination run of a transpose tile
+  int transpose_tbq = 0;  // 0 = auto; 16 / 32 = 16-byte items per destination run of a transpose tile
   // blocks below this size use TBQ = 16: 256^3 Float64 permutes go from 76 % to 94 % of the HBM
   // roofline, 1-2 GiB blocks are indifferent (profiles/r1_tile_sweep.txt)
   long long small_block_bytes = 256ll << 20;
