@@ -89,9 +89,9 @@ int pa_device_count(void);
  * (they are NVLink-bound; a capped, tile-striding grid leaves SMs to the local
  * kernels running beside them; n > 0 = n CTAs, n < 0 = |n| CTAs per SM (default
  * -4), 0 = uncapped), "box_copy_ctas" = same cap for pa_box_copy (benchmarks),
- * "nccl_fences" = 1: one-sided methods fence with NCCL groups, "nccl_register" = 1:
- * staging arenas from ncclMemAlloc + ncclCommRegister (set before the first
- * transpose!), "bulk_rows" = 1: row copies as the TMA bulk-copy pipeline,
+ * "nccl_fences" = 1: one-sided methods fence with NCCL groups, "nccl_register"
+ * (default 1; 0 = plain cudaMalloc arenas): staging arenas from ncclMemAlloc +
+ * ncclCommRegister, "bulk_rows" = 1: row copies as the TMA bulk-copy pipeline,
  * "transpose_tbq" / "small_block_bytes": transpose tile shape. */
 pa_status pa_set_tunable(const char* name, int64_t value);
 /* bind the calling thread to a device (one process per GPU: LOCAL_RANK).  All
