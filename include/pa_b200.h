@@ -73,8 +73,10 @@ typedef enum pa_method {
 typedef struct pa_topology pa_topology; /* MPITopology   (MPITopologies.jl:72-119) */
 typedef struct pa_pencil pa_pencil;     /* Pencil        (Pencils.jl:151-272)      */
 typedef struct pa_plan pa_plan;         /* Transposition (Transpositions.jl:69-119)*/
-typedef struct pa_comm pa_comm;         /* NCCL communicator standing in for
+typedef struct pa_comm pa_comm;         /* communicator standing in for
                                            topology.comm / subcomms               */
+typedef struct pa_host_chain pa_host_chain; /* asynchronous upload -> transpose!... ->
+                                           download pipeline for host arrays      */
 
 /* ---- library ------------------------------------------------------------- */
 const char* pa_version(void);
@@ -92,7 +94,17 @@ int pa_device_count(void);
  * "nccl_fences" = 1: one-sided methods fence with NCCL groups, "nccl_register"
  * (default 1; 0 = plain cudaMalloc arenas): staging arenas from ncclMemAlloc +
  * ncclCommRegister, "bulk_rows" = 1: row copies as the TMA bulk-copy pipeline,
- * "transpose_tbq" / "small_block_bytes": transpose tile shape. */
+ * "transpose_tbq" / "small_block_bytes": transpose tile shape,
+ * "multi_put" (default 1): the one-sided methods issue ONE launch over all peers'
+ * blocks with the window protocol inside the kernel, "p2p_chunks" (default 1):
+ * sub-blocks per peer block flowing pack -> exchange -> unpack independently
+ * (must be equal on all ranks), "staged_ctas": grid cap of pack/unpack kernels
+ * while an exchange is in flight, "ipc_exchange" = 1: the staged methods move the
+ * blocks with this library's own NVLink copy kernels instead of ncclSend/ncclRecv,
+ * "fence_timeout_ms" (default 60000): a flag wait longer than this records the
+ * failure and traps, "pdl" (default 1): programmatic dependent launch between
+ * back-to-back local kernels, "nccl_ctas": ncclCommInitRankConfig min/maxCTAs,
+ * "host_chunk_bytes": bytes per pipelined cut of the host paths.                 */
 pa_status pa_set_tunable(const char* name, int64_t value);
 /* bind the calling thread to a device (one process per GPU: LOCAL_RANK).  All
  * handles created afterwards (streams, staging arenas, communicator) live there. */
@@ -172,6 +184,9 @@ typedef struct pa_peer_info {
   int64_t recv_offset;   /* bytes into recv_buf; self block sits at the tail
                             (Transpositions.jl:393-403)                         */
   int64_t recv_count;    /* bytes                                               */
+  int64_t remote_recv_offset; /* bytes into the PEER's recv_buf where this rank's block
+                            lands (= that peer's recv_offset for me): the address the
+                            own-kernel exchange stores to (pa_plan_set_recv_window)  */
 } pa_peer_info;
 pa_status pa_plan_get_peer(const pa_plan* plan, int n /*1-based*/, pa_peer_info* info);
 
@@ -196,6 +211,12 @@ typedef struct pa_block_desc {
 } pa_block_desc;
 pa_status pa_plan_get_block(const pa_plan* plan, int op, int n /*1-based*/,
                             pa_block_desc* desc);
+/* sub-block `part` (0-based) of `nparts` of a pack (op 0) / unpack (op 1) block as the
+ * chunked PointToPoint schedule cuts it (tunable "p2p_chunks"): a sub-range of the
+ * block's outermost dimension, i.e. one contiguous piece of the wire block --
+ * [*wire_offset, *wire_offset + *wire_bytes) bytes into send_buf / recv_buf.     */
+pa_status pa_plan_get_chunk(const pa_plan* plan, int op, int n, int part, int nparts,
+                            pa_block_desc* desc, int64_t* wire_offset, int64_t* wire_bytes);
 
 /* ---- kernels (enqueue on `stream`; asynchronous) -------------------------
  * K1 pack: copy_range! (Transpositions.jl:552-583).  `buf` is the base of
@@ -214,6 +235,15 @@ pa_status pa_put(pa_plan* plan, int n, const void* src, void* peer_dst, void* st
 /* K2-get: the block peer n holds for this rank, loaded from `peer_src` = peer
  * n's src parent array (its layout) and stored permuted into `dst`.           */
 pa_status pa_get(pa_plan* plan, int n, const void* peer_src, void* dst, void* stream);
+/* K1-put / K2-get of EVERY remote block in ONE launch (the kernel the one-sided
+ * methods run, here without the window protocol): `peers[n-1]` = peer n's dest
+ * (put) / src (get) parent array, the self entry is ignored.  Tiles of the blocks
+ * are interleaved round-robin so that all destination links are driven at once.
+ * `max_ctas`: grid cap (0 = tunable "remote_ctas").  Falls back to one launch per
+ * block when the blocks need different kernel flavours.                        */
+pa_status pa_put_all(pa_plan* plan, const void* src, void* const* peers, int max_ctas,
+                     void* stream);
+pa_status pa_get_all(pa_plan* plan, void* const* peers, void* dst, int max_ctas, void* stream);
 /* transpose_impl!(::Nothing) / permute_local! (:213-270).  `scratch` must hold
  * length_out elements when src and dst alias, may be NULL otherwise.        */
 pa_status pa_permute_local(pa_plan* plan, const void* src, void* dst,
@@ -230,12 +260,20 @@ pa_status pa_box_copy(int nd, const int64_t* extent, const int64_t* src_stride,
  * pa_comm_unique_id and distributes the 128 bytes by any side channel.      */
 pa_status pa_comm_unique_id(void* id128);
 pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** out);
+/* NCCL-free communicator: ranks talk only through peer-mapped memory (CUDA IPC) and
+ * the flag window below, which is then mandatory.  Serves PA_PEER_PUT / PA_PEER_GET
+ * as they are and the staged methods through the library's own NVLink copy kernels
+ * (pa_plan_set_recv_window).  Unlike NCCL it also allows several ranks on ONE device
+ * (test rigs; a single-GPU box can exercise the whole multi-rank path).          */
+pa_status pa_comm_init_local(int nranks, int rank, pa_comm** out);
 void pa_comm_destroy(pa_comm* c);
-/* Optional flag window of the one-sided methods: each rank exports a small
- * device buffer (one 64-bit word per source rank) and imports everybody
- * else's; the fences of PA_PEER_PUT / PA_PEER_GET then become one tiny kernel
- * (st.release.sys to the peers + ld.acquire.sys polling, 10 s time-out) instead
- * of an NCCL send/recv group.  Without it the NCCL fences are used.           */
+/* Flag window: each rank exports a small device buffer (a few 64-bit words per
+ * source rank) and imports everybody else's.  Words only increase (signals are
+ * red.max.release.sys over NVLink, waits are ld.acquire.sys polls with the
+ * "fence_timeout_ms" time-out): window-open / window-close of PA_PEER_PUT /
+ * PA_PEER_GET ride inside the transfer kernel, block arrival of the own-kernel
+ * exchange is one word per peer.  Without it (NCCL communicators only) the
+ * one-sided methods fence with NCCL send/recv groups.                          */
 pa_status pa_comm_flags_export(pa_comm* c, void* handle64, int64_t* offset);
 pa_status pa_comm_flags_import(pa_comm* c, int rank, const void* handle64, int64_t offset);
 
@@ -247,11 +285,19 @@ pa_status pa_comm_flags_import(pa_comm* c, int rank, const void* handle64, int64
 #define PA_IPC_HANDLE_BYTES 64
 /* handle of the device allocation containing `devptr` + byte offset of devptr in it */
 pa_status pa_ipc_export(const void* devptr, void* handle64, int64_t* offset);
-/* map a peer's allocation (cached per handle) and return base + offset */
+/* map a peer's allocation (one mapping per handle, reference-counted) and return
+ * base + offset; every successful import is paired with one pa_ipc_release     */
 pa_status pa_ipc_import(const void* handle64, int64_t offset, void** mapped);
+/* drop one reference; the mapping is closed (cudaIpcCloseMemHandle) with the last */
+pa_status pa_ipc_release(const void* handle64);
 /* `peer_dst` = peer n's (1-based index in the grid line) dest array as mapped here;
  * `local_dst` = this rank's dest array the window belongs to                   */
 pa_status pa_plan_set_window(pa_plan* plan, const void* local_dst, int n, void* peer_dst);
+/* own-kernel exchange of the staged methods (NCCL-free communicator, or tunable
+ * "ipc_exchange"): `peer_recv_buf` = peer n's recv_buf arena (pa_pencil_buffers
+ * after pa_pencil_reserve, exported with pa_ipc_export) as mapped here.  Must be
+ * renewed when the arenas are reallocated (PA_ESTATE otherwise).                */
+pa_status pa_plan_set_recv_window(pa_plan* plan, int n, void* peer_recv_buf);
 
 /* ---- transpose! ----------------------------------------------------------
  * transpose!(t; waitall) (Transpositions.jl:170-179) for device arrays.
@@ -263,9 +309,38 @@ pa_status pa_transpose(pa_plan* plan, pa_comm* comm, const void* src, void* dst,
                        unsigned flags, void* stream);
 pa_status pa_wait(pa_plan* plan, void* stream);
 /* same, with HOST arrays: H2D of `src`, transpose!, D2H of `dst`; blocks until
- * `host_dst` is valid.  Device staging is owned by the plan.                 */
+ * `host_dst` is valid.  Device staging is owned by the plan.  A purely local
+ * transposition (nproc == 1 or dim == nothing) is cut along the source's outermost
+ * dimension and pipelined on three streams: upload(c+1) || kernel(c) ||
+ * download(c-1) (the download joins when that dimension is outermost in `dst` too).
+ * Pinning the host arrays (cudaHostRegister / pinned allocation) is the caller's job. */
 pa_status pa_transpose_host(pa_plan* plan, pa_comm* comm, const void* host_src,
                             void* host_dst, unsigned flags);
+
+/* ---- host chains -----------------------------------------------------------
+ * A sequence of transpositions applied to HOST arrays (plan i+1 consumes what
+ * plan i produces): one submit = upload of `host_src`, every transpose! on the
+ * device, download into `host_dst`.  Submits return immediately and are double-
+ * buffered on the device: the download of one overlaps the upload of the next
+ * (PCIe is full duplex).  pa_host_chain_wait(ticket) blocks until that submit's
+ * `host_dst` is valid (ticket < 0: all).  The host arrays must stay untouched /
+ * alive until then.  For the one-sided methods the device buffers the plans will
+ * see are exposed through pa_host_chain_buffer(slot 0..1, which 0..1) so that
+ * windows can be registered on them (plan i of a submit in slot s reads buffer
+ * (s, i % 2) and writes buffer (s, 1 - i % 2)).                                  */
+pa_status pa_host_chain_create(int n, pa_plan* const* plans, pa_comm* comm,
+                               pa_host_chain** out);
+void pa_host_chain_destroy(pa_host_chain* c);
+pa_status pa_host_chain_submit(pa_host_chain* c, const void* host_src, void* host_dst,
+                               int64_t* ticket /* out, may be NULL */);
+pa_status pa_host_chain_wait(pa_host_chain* c, int64_t ticket);
+pa_status pa_host_chain_buffer(pa_host_chain* c, int slot, int which, void** devptr,
+                               int64_t* bytes);
+/* CUDA-event bracket around a run of submits (device-side timing of the pipeline):
+ * begin marks the upload stream now, end waits for everything submitted so far and
+ * returns the milliseconds between the two.                                      */
+pa_status pa_host_chain_time_begin(pa_host_chain* c);
+pa_status pa_host_chain_time_end(pa_host_chain* c, float* ms);
 
 /* CUDA-event timings (ms) of the last pa_transpose on this plan, named after
  * the reference's TimerOutputs sections (Transpositions.jl:172-175,326,336).

@@ -23,7 +23,7 @@ from .arrays import (PencilArray, ManyPencilArray, parent, pencil, extra_dims, n
                      size_local, similar)
 from . import transpositions as Transpositions
 from .transpositions import (Transposition, transpose_, transpose_bang, Waitall, PointToPoint,
-                             Alltoallv, PeerPut, PeerGet)
+                             Alltoallv, PeerPut, PeerGet, HostChain, transpose_host_, set_tunable)
 
 
 def launch_count() -> int:

@@ -44,6 +44,7 @@ class PeerInfo(C.Structure):
         ("world_rank", C.c_int), ("is_self", C.c_int),
         ("send_offset", C.c_int64), ("send_count", C.c_int64),
         ("recv_offset", C.c_int64), ("recv_count", C.c_int64),
+        ("remote_recv_offset", C.c_int64),
     ]
 
 
@@ -92,25 +93,39 @@ SIGNATURES = {
     "pa_plan_get_info": (C.c_int, [_P, C.POINTER(PlanInfo)]),
     "pa_plan_get_peer": (C.c_int, [_P, C.c_int, C.POINTER(PeerInfo)]),
     "pa_plan_get_block": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(BlockDesc)]),
+    "pa_plan_get_chunk": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(BlockDesc),
+                                    _I64P, _I64P]),
     "pa_pack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_unpack": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_put": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "pa_get": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "pa_put_all": (C.c_int, [_P, _P, C.POINTER(_P), C.c_int, _P]),
+    "pa_get_all": (C.c_int, [_P, C.POINTER(_P), _P, C.c_int, _P]),
     "pa_copy_self": (C.c_int, [_P, _P, _P, _P]),
     "pa_permute_local": (C.c_int, [_P, _P, _P, _P, _P]),
     "pa_box_copy": (C.c_int, [C.c_int, _I64P, _I64P, _I64P, C.c_int, _P, _P, _P,
                               C.POINTER(BlockDesc)]),
     "pa_comm_unique_id": (C.c_int, [_P]),
     "pa_comm_init_rank": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "pa_comm_init_local": (C.c_int, [C.c_int, C.c_int, C.POINTER(_P)]),
     "pa_comm_destroy": (None, [_P]),
     "pa_comm_flags_export": (C.c_int, [_P, _P, _I64P]),
     "pa_comm_flags_import": (C.c_int, [_P, C.c_int, _P, C.c_int64]),
     "pa_ipc_export": (C.c_int, [_P, _P, _I64P]),
     "pa_ipc_import": (C.c_int, [_P, C.c_int64, C.POINTER(_P)]),
+    "pa_ipc_release": (C.c_int, [_P]),
     "pa_plan_set_window": (C.c_int, [_P, _P, C.c_int, _P]),
+    "pa_plan_set_recv_window": (C.c_int, [_P, C.c_int, _P]),
     "pa_transpose": (C.c_int, [_P, _P, _P, _P, C.c_uint, _P]),
     "pa_wait": (C.c_int, [_P, _P]),
     "pa_transpose_host": (C.c_int, [_P, _P, _P, _P, C.c_uint]),
+    "pa_host_chain_create": (C.c_int, [C.c_int, C.POINTER(_P), _P, C.POINTER(_P)]),
+    "pa_host_chain_destroy": (None, [_P]),
+    "pa_host_chain_submit": (C.c_int, [_P, _P, _P, _I64P]),
+    "pa_host_chain_wait": (C.c_int, [_P, C.c_int64]),
+    "pa_host_chain_time_begin": (C.c_int, [_P]),
+    "pa_host_chain_time_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "pa_host_chain_buffer": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I64P]),
     "pa_plan_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "pa_plan_enable_timing": (C.c_int, [_P, C.c_int]),
 }

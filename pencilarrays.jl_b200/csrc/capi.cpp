@@ -2,6 +2,7 @@
 // the reference's 1-based / inclusive conventions and the 0-based internals.
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "pa_internal.hpp"
 
@@ -20,7 +21,7 @@ using namespace pa;
 
 extern "C" {
 
-const char* pa_version(void) { return "pa_b200 0.1.0 (sm_100a)"; }
+const char* pa_version(void) { return "pa_b200 0.2.0 (sm_100a)"; }
 
 const char* pa_strerror(pa_status s) {
   switch (s) {
@@ -57,6 +58,14 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   else if (!strcmp(name, "nccl_register")) g_tun.nccl_register = (int)value;
   else if (!strcmp(name, "transpose_tbq")) g_tun.transpose_tbq = (int)value;
   else if (!strcmp(name, "small_block_bytes")) g_tun.small_block_bytes = value;
+  else if (!strcmp(name, "multi_put")) g_tun.multi_put = (int)value;
+  else if (!strcmp(name, "p2p_chunks")) g_tun.p2p_chunks = (int)value;
+  else if (!strcmp(name, "staged_ctas")) g_tun.staged_ctas = (int)value;
+  else if (!strcmp(name, "ipc_exchange")) g_tun.ipc_exchange = (int)value;
+  else if (!strcmp(name, "fence_timeout_ms")) g_tun.fence_timeout_ms = value;
+  else if (!strcmp(name, "pdl")) g_tun.pdl = (int)value;
+  else if (!strcmp(name, "nccl_ctas")) g_tun.nccl_ctas = (int)value;
+  else if (!strcmp(name, "host_chunk_bytes")) g_tun.host_chunk_bytes = value;
   else {
     set_error("unknown tunable '%s'", name);
     return PA_EINVAL;
@@ -332,6 +341,7 @@ pa_status pa_plan_get_peer(const pa_plan* plan, int n, pa_peer_info* info) {
   info->send_count = pr.send_cnt * S;
   info->recv_offset = pr.recv_off * S;
   info->recv_count = pr.recv_cnt * S;
+  info->remote_recv_offset = pr.remote_recv_off * S;
   return PA_OK;
 }
 
@@ -362,6 +372,23 @@ pa_status pa_plan_get_block(const pa_plan* plan, int op, int n, pa_block_desc* d
   }
   const Peer& pr = P.peers[n - 1];
   export_block(op == 0 ? pr.pack : op == 1 ? pr.unpack : op == 3 ? pr.put : pr.get, desc);
+  return PA_OK;
+}
+
+pa_status pa_plan_get_chunk(const pa_plan* plan, int op, int n, int part, int nparts,
+                            pa_block_desc* desc, int64_t* wire_offset, int64_t* wire_bytes) {
+  if (!plan || !desc) return PA_EINVAL;
+  const Plan& P = *plan->p;
+  if (P.dim < 0 || n < 1 || n > P.nproc || op < 0 || op > 1 || nparts < 1 || part < 0 ||
+      part >= nparts) {
+    set_error("bad chunk selector (op=%d, n=%d, part=%d/%d)", op, n, part, nparts);
+    return PA_EINVAL;
+  }
+  const Peer& pr = P.peers[n - 1];
+  const BlockCopy c = sub_block(op == 0 ? pr.pack : pr.unpack, part, nparts, op == 0, nullptr, nullptr);
+  export_block(c, desc);
+  if (wire_offset) *wire_offset = (op == 0 ? c.dst_off : c.src_off) * c.elsize;
+  if (wire_bytes) *wire_bytes = c.count * c.elsize;
   return PA_OK;
 }
 
@@ -420,6 +447,48 @@ pa_status pa_get(pa_plan* plan, int n, const void* peer_src, void* dst, void* st
   pa_status s = need_gpu();
   if (s != PA_OK) return s;
   return launch_block(P.peers[n - 1].get, peer_src, dst, stream, nullptr);
+}
+
+static pa_status all_blocks(pa_plan* plan, bool get, const void* local, void* const* peers,
+                            int max_ctas, void* stream) {
+  if (!plan || !peers) return PA_EINVAL;
+  Plan& P = *plan->p;
+  if (P.dim < 0) {
+    set_error("plan has no exchange");
+    return PA_EINVAL;
+  }
+  pa_status s = need_gpu();
+  if (s != PA_OK) return s;
+  std::vector<const BlockCopy*> blocks;
+  std::vector<const void*> srcs;
+  std::vector<void*> dsts;
+  for (int k = 1; k < P.nproc; ++k) {
+    const int n = get ? (P.self_index - k + P.nproc) % P.nproc : (P.self_index + k) % P.nproc;
+    const BlockCopy& b = get ? P.peers[n].get : P.peers[n].put;
+    if (b.klass == KC_EMPTY) continue;
+    blocks.push_back(&b);
+    srcs.push_back(get ? (const void*)peers[n] : local);
+    dsts.push_back(get ? (void*)local : peers[n]);
+  }
+  if (blocks.empty()) return PA_OK;
+  if (max_ctas == 0) max_ctas = g_tun.remote_ctas;
+  s = launch_multi((int)blocks.size(), blocks.data(), srcs.data(), dsts.data(), stream, max_ctas,
+                   nullptr);
+  if (s != PA_EINCOMPAT) return s;
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    s = launch_block(*blocks[i], srcs[i], dsts[i], stream, nullptr, max_ctas);
+    if (s != PA_OK) return s;
+  }
+  return PA_OK;
+}
+
+pa_status pa_put_all(pa_plan* plan, const void* src, void* const* peers, int max_ctas,
+                     void* stream) {
+  GUARD({ return all_blocks(plan, false, src, peers, max_ctas, stream); })
+}
+
+pa_status pa_get_all(pa_plan* plan, void* const* peers, void* dst, int max_ctas, void* stream) {
+  GUARD({ return all_blocks(plan, true, dst, peers, max_ctas, stream); })
 }
 
 pa_status pa_copy_self(pa_plan* plan, const void* src, void* dst, void* stream) {
@@ -488,6 +557,17 @@ pa_status pa_comm_init_rank(const void* id128, int nranks, int rank, pa_comm** o
   })
 }
 
+pa_status pa_comm_init_local(int nranks, int rank, pa_comm** out) {
+  GUARD({
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return PA_EINVAL;
+    Comm* c = nullptr;
+    pa_status s = comm_init_local(nranks, rank, &c);
+    if (s != PA_OK) return s;
+    *out = new pa_comm{c};
+    return PA_OK;
+  })
+}
+
 pa_status pa_comm_flags_export(pa_comm* c, void* handle64, int64_t* offset) {
   if (!c || !handle64 || !offset) return PA_EINVAL;
   return comm_flags_export(c->p, handle64, offset);
@@ -519,10 +599,25 @@ pa_status pa_ipc_import(const void* handle64, int64_t offset, void** mapped) {
   })
 }
 
+pa_status pa_ipc_release(const void* handle64) {
+  GUARD({
+    if (!handle64) return PA_EINVAL;
+    return ipc_release_handle(handle64);
+  })
+}
+
 pa_status pa_plan_set_window(pa_plan* plan, const void* local_dst, int n, void* peer_dst) {
   GUARD({
-    if (!plan || !local_dst) return PA_EINVAL;
+    // local_dst may be NULL: a rank that owns nothing of `dest` still puts into its peers
+    if (!plan) return PA_EINVAL;
     return plan_set_window(plan->p, local_dst, n - 1, peer_dst);
+  })
+}
+
+pa_status pa_plan_set_recv_window(pa_plan* plan, int n, void* peer_recv_buf) {
+  GUARD({
+    if (!plan) return PA_EINVAL;
+    return plan_set_recv_window(plan->p, n - 1, peer_recv_buf);
   })
 }
 
@@ -530,10 +625,11 @@ pa_status pa_plan_set_window(pa_plan* plan, const void* local_dst, int n, void* 
 pa_status pa_transpose(pa_plan* plan, pa_comm* comm, const void* src, void* dst, unsigned flags,
                        void* stream) {
   GUARD({
-    if (!plan || !src || !dst) {
-      set_error("pa_transpose: null argument");
+    if (!plan) {
+      set_error("pa_transpose: null plan");
       return PA_EINVAL;
     }
+    // src / dst may be NULL on a rank whose local array is empty (checked against the plan)
     return transpose(plan->p, comm ? comm->p : nullptr, src, dst, flags, stream);
   })
 }
@@ -546,9 +642,63 @@ pa_status pa_wait(pa_plan* plan, void* stream) {
 pa_status pa_transpose_host(pa_plan* plan, pa_comm* comm, const void* host_src, void* host_dst,
                             unsigned flags) {
   GUARD({
-    if (!plan || !host_src || !host_dst) return PA_EINVAL;
+    if (!plan) return PA_EINVAL;
     return transpose_host(plan->p, comm ? comm->p : nullptr, host_src, host_dst, flags);
   })
+}
+
+pa_status pa_host_chain_create(int n, pa_plan* const* plans, pa_comm* comm, pa_host_chain** out) {
+  GUARD({
+    if (n < 1 || n > 64 || !plans || !out) {
+      set_error("pa_host_chain_create: 1..64 plans");
+      return PA_EINVAL;
+    }
+    Plan* ps[64];
+    for (int i = 0; i < n; ++i) {
+      if (!plans[i]) return PA_EINVAL;
+      ps[i] = plans[i]->p;
+    }
+    HostChain* c = nullptr;
+    pa_status s = host_chain_create(n, ps, comm ? comm->p : nullptr, &c);
+    if (s != PA_OK) return s;
+    *out = new pa_host_chain{c};
+    return PA_OK;
+  })
+}
+
+void pa_host_chain_destroy(pa_host_chain* c) {
+  if (!c) return;
+  host_chain_destroy(c->p);
+  delete c;
+}
+
+pa_status pa_host_chain_submit(pa_host_chain* c, const void* host_src, void* host_dst,
+                               int64_t* ticket) {
+  GUARD({
+    if (!c) return PA_EINVAL;
+    return host_chain_submit(c->p, host_src, host_dst, ticket);
+  })
+}
+
+pa_status pa_host_chain_wait(pa_host_chain* c, int64_t ticket) {
+  if (!c) return PA_EINVAL;
+  return host_chain_wait(c->p, ticket);
+}
+
+pa_status pa_host_chain_time_begin(pa_host_chain* c) {
+  if (!c) return PA_EINVAL;
+  return host_chain_time_begin(c->p);
+}
+
+pa_status pa_host_chain_time_end(pa_host_chain* c, float* ms) {
+  if (!c || !ms) return PA_EINVAL;
+  return host_chain_time_end(c->p, ms);
+}
+
+pa_status pa_host_chain_buffer(pa_host_chain* c, int slot, int which, void** devptr,
+                               int64_t* bytes) {
+  if (!c) return PA_EINVAL;
+  return host_chain_buffer(c->p, slot, which, devptr, bytes);
 }
 
 pa_status pa_plan_timings(pa_plan* plan, pa_timings* t) {

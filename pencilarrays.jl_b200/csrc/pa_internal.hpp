@@ -41,7 +41,9 @@ struct Buffers {
   i64 send_cap = 0;
   void* recv = nullptr;
   i64 recv_cap = 0;
-  void* comm_done_event = nullptr;  // cudaEvent_t of the last exchange using them
+  void* comm_done_event = nullptr;    // cudaEvent_t of the last exchange using them
+  void* unpack_done_event = nullptr;  // cudaEvent_t of the last unpack that READ recv (or wrote it locally)
+  unsigned long long generation = 0;  // bumped whenever an arena is (re)allocated: stale peer windows are refused
   // NCCL user-buffer registration (tunable "nccl_register"): arenas come from
   // ncclMemAlloc and are registered with the communicator so that ncclSend /
   // ncclRecv can go zero-copy over NVLink instead of through NCCL's staging FIFO
@@ -90,28 +92,61 @@ enum KernelClass { KC_EMPTY = 0, KC_ROWS = 1, KC_TRANSPOSE = 2, KC_TILE_SCALAR =
 // src[off_s + sum k_i ss_i]` for k in the box.  dims[0] = X (smallest source
 // stride), dims[1] = Y (the tile's second dim), the rest are outer dims.
 struct BlockCopy {
-  // as given (source memory order), kept for pa_plan_get_block
+  // as given (source memory order), kept for pa_plan_get_block; one spare slot for
+  // the innermost word pseudo-dimension of non-power-of-two element sizes
   int nd_raw = 0;
-  Dim raw[PA_MAX_DIMS];
+  Dim raw[PA_MAX_DIMS + 1];
   i64 src_off = 0, dst_off = 0;  // elements
   int elsize = 0;
   i64 count = 0;                 // elements in the box
 
   // canonical form
   int nd = 0;
-  Dim d[PA_MAX_DIMS];
+  Dim d[PA_MAX_DIMS + 1];
   int klass = KC_EMPTY;
   int stride_align = 16;  // largest power of two (<=16) dividing every byte stride / run length
+  int src_align = 16;     // same, source side only (row starts / run lengths of the loads)
+  int dst_align = 16;     // same, destination side only
   bool contiguous_both = false;  // whole block is one contiguous run on both sides
 };
 
 void canonicalize(BlockCopy& b);
+// sub-block [c0, c1) of the OUTERMOST raw dim with extent > 1 (chunked pipelining of
+// a peer block: the chunk is a contiguous sub-range of the dense side); returns the
+// element offset of the chunk inside the dense side through *dense_off, its length
+// through *dense_cnt
+BlockCopy sub_block(const BlockCopy& b, int part, int nparts, bool dense_is_dst, i64* dense_off,
+                    i64* dense_cnt);
 
 // launch on `stream`; src/dst are array base pointers (offsets come from b)
 // max_ctas > 0 caps the grid (CTAs then stride over the tiles): used for the
 // NVLink-bound remote kernels so that they leave SMs to concurrent local work.
 pa_status launch_block(const BlockCopy& b, const void* src, void* dst, void* stream,
-                       int* vec_used, int max_ctas = 0);
+                       int* vec_used, int max_ctas = 0, bool pdl = false);
+
+// Flag words of the one-sided protocols (NVLink signals between the ranks of a
+// grid line): a set of (peer's word for me, my word for the peer, sequence number).
+constexpr int FLAG_INLINE_MAX = 8;  // peers handled inside one multi-peer launch (one NVSwitch box: <= 7)
+struct FlagSet {
+  int n;
+  unsigned long long* remote[FLAG_INLINE_MAX];
+  unsigned long long* local[FLAG_INLINE_MAX];
+  unsigned long long seq[FLAG_INLINE_MAX];
+};
+struct MultiFlags {
+  FlagSet ready;  // prologue: signal + wait ("the other side of every block may be touched")
+  FlagSet done;   // epilogue: the last CTA signals ("all my blocks have landed / been read")
+  int wait_done;           // the last CTA also waits for every peer's `done` before exiting
+  unsigned int* counter;   // device word counting finished CTAs (reset by the last one)
+  unsigned long long timeout_ns;
+  int* err;
+};
+// ONE launch executing up to FLAG_INLINE_MAX box copies of the same kernel flavour,
+// tiles interleaved round-robin over the blocks so that every destination link is
+// driven at once; optional in-kernel ready/done protocol (mf may be NULL).
+// Returns PA_EINCOMPAT (without launching) when the blocks need different kernels.
+pa_status launch_multi(int nb, const BlockCopy* const* blocks, const void* const* srcs,
+                       void* const* dsts, void* stream, int max_ctas, const MultiFlags* mf);
 
 // run-time tunables (pa_set_tunable)
 struct Tunables {
@@ -126,6 +161,15 @@ struct Tunables {
   int nccl_register = 1;  // staging arenas from ncclMemAlloc + ncclCommRegister (registered NCCL p2p:
                           // exchange 637 -> 673 GB/s at N=2); falls back to cudaMalloc when unavailable
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
+  int multi_put = 1;     // 1: one launch interleaving every peer's tiles (+ in-kernel flags) on the one-sided paths
+  int p2p_chunks = 1;    // staged schedules: sub-blocks per peer block (pack-chunk -> send-chunk -> unpack-chunk)
+  int staged_ctas = 0;   // grid cap of pack/unpack kernels while an exchange is in flight (0 = uncapped, <0 per SM)
+  int ipc_exchange = 0;  // 1: staged schedules move the blocks with this library's own NVLink copy kernels
+                         //    (peer-mapped recv_buf + flag signals) even when an NCCL communicator exists
+  long long fence_timeout_ms = 60000;  // a flag wait longer than this sets the error word and traps
+  int pdl = 1;           // programmatic dependent launch between the back-to-back kernels of a chain
+  int nccl_ctas = 0;     // > 0: ncclCommInitRankConfig min/maxCTAs
+  long long host_chunk_bytes = 64ll << 20;  // pa_transpose_host: bytes per pipelined chunk
 };
 extern Tunables g_tun;
 
@@ -139,6 +183,7 @@ struct Peer {
   BlockCopy unpack;  // K2: contiguous @ recv_off -> dest parent box
   BlockCopy put;     // K1-put: src parent box -> the PEER's dest parent (its layout), no staging
   BlockCopy get;     // K2-get: the PEER's src parent box (its layout) -> dest parent box
+  i64 remote_recv_off = 0;  // elements: where MY block starts inside the PEER's recv_buf
 };
 
 struct TransposeState;  // streams/events, defined in transpose.cpp
@@ -162,9 +207,13 @@ struct Plan {
   // PeerPut windows: local dest base pointer -> peer-mapped dest base pointers
   // (indexed by position in the grid line; nullptr for self)
   std::map<const void*, std::vector<void*>> windows;
+  // windows on the peers' recv_buf arenas (own-kernel exchange of the staged schedules)
+  std::vector<void*> recv_windows;
+  unsigned long long recv_windows_gen = 0;  // generation of MY arenas when they were registered
   // host-transpose staging
   void* h_src_dev = nullptr;
   void* h_dst_dev = nullptr;
+  i64 h_src_cap = 0, h_dst_cap = 0;
   ~Plan();
 };
 
@@ -175,6 +224,7 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
 struct Comm;
 pa_status comm_unique_id(void* id128);
 pa_status comm_init(const void* id128, int nranks, int rank, Comm** out);
+pa_status comm_init_local(int nranks, int rank, Comm** out);  // no NCCL: flag window + peer mappings only
 void comm_destroy(Comm* c);
 pa_status comm_flags_export(Comm* c, void* handle64, i64* offset);
 pa_status comm_flags_import(Comm* c, int rank, const void* handle64, i64 offset);
@@ -191,11 +241,30 @@ void destroy_state(TransposeState* st);
 // CUDA IPC plumbing of the PeerPut method (one-sided puts over NVLink)
 pa_status ipc_export(const void* devptr, void* handle64, i64* offset);
 pa_status ipc_import(const void* handle64, i64 offset, void** mapped);
+pa_status ipc_release_handle(const void* handle64);
 pa_status plan_set_window(Plan* plan, const void* local_dst, int n0, void* peer_dst);
+pa_status plan_set_recv_window(Plan* plan, int n0, void* peer_recv_buf);
+
+// host pipelines (pa_host_chain_*)
+struct HostChain;
+pa_status host_chain_create(int n, Plan* const* plans, Comm* comm, HostChain** out);
+void host_chain_destroy(HostChain* c);
+pa_status host_chain_submit(HostChain* c, const void* hsrc, void* hdst, i64* ticket);
+pa_status host_chain_wait(HostChain* c, i64 ticket);
+pa_status host_chain_buffer(HostChain* c, int slot, int which, void** p, i64* bytes);
+pa_status host_chain_time_begin(HostChain* c);
+pa_status host_chain_time_end(HostChain* c, float* ms);
+
+// standalone flag step on `stream`: signal the n remote words (monotonic max,
+// release at system scope) and/or wait for the n local words to reach seq
+pa_status launch_flags(int n, unsigned long long* const* remote, unsigned long long* const* local,
+                       const unsigned long long* seq, bool do_signal, bool do_wait,
+                       unsigned long long timeout_ns, int* err, void* stream);
 
 int device_count();
 pa_status set_device(int dev);
 i64 launch_count();
+void count_launch();
 
 }  // namespace pa
 
@@ -203,3 +272,4 @@ struct pa_topology { std::shared_ptr<pa::Topology> p; };
 struct pa_pencil { std::shared_ptr<pa::Pencil> p; };
 struct pa_plan { pa::Plan* p; };
 struct pa_comm { pa::Comm* p; };
+struct pa_host_chain { pa::HostChain* p; };

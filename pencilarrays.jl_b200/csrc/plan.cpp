@@ -78,7 +78,7 @@ void canonicalize(BlockCopy& b) {
   b.contiguous_both = false;
   if (b.count == 0) return;
 
-  Dim t[PA_MAX_DIMS];
+  Dim t[PA_MAX_DIMS + 1];
   int n = 0;
   for (int i = 0; i < b.nd_raw; ++i)
     if (b.raw[i].e != 1) t[n++] = b.raw[i];
@@ -113,29 +113,71 @@ void canonicalize(BlockCopy& b) {
   for (int i = 0; i < n; ++i) b.d[i] = t[i];
   b.contiguous_both = (n == 1 && t[0].ss == 1 && t[0].ds == 1);
 
-  // largest power-of-two access width every stride / run length allows
+  // largest power-of-two access width every stride / run length allows, per side:
+  // the source side constrains the loads, the destination side the stores
   const i64 S = b.elsize;
-  int al = 16;
+  int sa = 16, da = 16;
   if (b.klass == KC_ROWS) {
-    al = std::min(al, pow2_divisor(t[0].e * S, 16));
+    sa = da = pow2_divisor(t[0].e * S, 16);
     for (int i = 1; i < n; ++i) {
-      al = std::min(al, pow2_divisor(t[i].ss * S, 16));
-      al = std::min(al, pow2_divisor(t[i].ds * S, 16));
+      sa = std::min(sa, pow2_divisor(t[i].ss * S, 16));
+      da = std::min(da, pow2_divisor(t[i].ds * S, 16));
     }
   } else if (b.klass == KC_TRANSPOSE) {
-    // vector path needs whole 16-byte vectors along X (source) and Y (dest)
-    al = std::min(al, pow2_divisor(t[0].e * S, 16));
-    al = std::min(al, pow2_divisor(t[1].e * S, 16));
-    al = std::min(al, pow2_divisor(t[0].ds * S, 16));
-    al = std::min(al, pow2_divisor(t[1].ss * S, 16));
+    // whole 16-byte vectors along X on the source side, along Y on the destination side
+    sa = std::min(sa, pow2_divisor(t[0].e * S, 16));
+    sa = std::min(sa, pow2_divisor(t[1].ss * S, 16));
+    da = std::min(da, pow2_divisor(t[1].e * S, 16));
+    da = std::min(da, pow2_divisor(t[0].ds * S, 16));
     for (int i = 2; i < n; ++i) {
-      al = std::min(al, pow2_divisor(t[i].ss * S, 16));
-      al = std::min(al, pow2_divisor(t[i].ds * S, 16));
+      sa = std::min(sa, pow2_divisor(t[i].ss * S, 16));
+      da = std::min(da, pow2_divisor(t[i].ds * S, 16));
     }
   } else {
-    al = (int)std::min<i64>(S, 16);
+    sa = da = (int)std::min<i64>(S, 16);
   }
-  b.stride_align = al;
+  b.src_align = sa;
+  b.dst_align = da;
+  b.stride_align = std::min(sa, da);
+}
+
+// Chunk `part` of `nparts` along the outermost raw dim with extent > 1.  The dense
+// side of a pack (dst) / unpack (src) block lists its dims in the same order, so
+// the chunk is one contiguous sub-range of it, and sender and receiver -- who see
+// the same box -- cut it at the same places.
+BlockCopy sub_block(const BlockCopy& b, int part, int nparts, bool dense_is_dst, i64* dense_off,
+                    i64* dense_cnt) {
+  BlockCopy c = b;
+  int j = -1;
+  for (int i = b.nd_raw - 1; i >= 0; --i)
+    if (b.raw[i].e > 1) {
+      j = i;
+      break;
+    }
+  if (b.count == 0 || j < 0) {
+    // nothing to cut: the whole block is part 0
+    if (part != 0) {
+      for (int i = 0; i < c.nd_raw; ++i) c.raw[i].e = (i == 0) ? 0 : c.raw[i].e;
+      if (c.nd_raw == 0) {
+        c.nd_raw = 1;
+        c.raw[0] = Dim{0, 1, 1};
+      }
+    }
+    canonicalize(c);
+    if (dense_off) *dense_off = 0;
+    if (dense_cnt) *dense_cnt = c.count;
+    return c;
+  }
+  const i64 e = b.raw[j].e;
+  const i64 c0 = e * part / nparts, c1 = e * (part + 1) / nparts;
+  c.raw[j].e = c1 - c0;
+  c.src_off += c0 * b.raw[j].ss;
+  c.dst_off += c0 * b.raw[j].ds;
+  canonicalize(c);
+  const i64 dense_stride = dense_is_dst ? b.raw[j].ds : b.raw[j].ss;
+  if (dense_off) *dense_off = c0 * dense_stride;
+  if (dense_cnt) *dense_cnt = (c1 - c0) * dense_stride;
+  return c;
 }
 
 // ---- plan -------------------------------------------------------------------
@@ -202,6 +244,16 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
   if (elsize <= 0) {
     set_error("invalid element size %d", elsize);
     return PA_EINVAL;
+  }
+  {
+    // an element size that is not a power of two <= 16 costs one more (innermost) dimension
+    int w = 1;
+    while (w < 16 && elsize % (2 * w) == 0) w *= 2;
+    if (elsize / w > 1 && Pi.N + n_extra + 1 > PA_MAX_DIMS) {
+      set_error("too many dimensions for %d-byte elements: N + n_extra must be <= %d", elsize,
+                PA_MAX_DIMS - 1);
+      return PA_EINVAL;
+    }
   }
   if (method < PA_POINT_TO_POINT || method > PA_PEER_GET) {
     set_error("unknown transposition method %d", method);
@@ -363,6 +415,22 @@ pa_status build_plan(std::shared_ptr<Pencil> pin, std::shared_ptr<Pencil> pout, 
       Lsrc = &Lpin;
       pr.get = make_block(rlo, rhi, false, false, 0, 0);
       Lsrc = &Li;
+      // where my block lands inside peer n's recv_buf: behind the blocks of the
+      // sources that precede me in the line (remote blocks in increasing source
+      // index, :380-416 as seen from the receiver)
+      i64 off = 0, c2[PA_MAX_TOPO];
+      for (int i = 0; i < T.M; ++i) c2[i] = T.coords[i];
+      for (int m = 0; m < P->self_index; ++m) {
+        if (m == n) continue;
+        c2[dim] = m;
+        i64 mlo[PA_MAX_DIMS], mhi[PA_MAX_DIMS];
+        Pi.range_of(c2, mlo, mhi);
+        i64 cnt = P->prod_extra;
+        for (int d = 0; d < N; ++d)
+          cnt *= std::max<i64>(0, std::min(ohi[d], mhi[d]) - std::max(olo[d], mlo[d]));
+        off += cnt;
+      }
+      pr.remote_recv_off = off;
     }
   }
   if (isend != P->send_elems || irecv != length_recv) {

@@ -66,6 +66,16 @@ class PeerGet(AbstractTransposeMethod):
     code = _lib.PA_PEER_GET
 
 
+_tunables = {}
+
+
+def set_tunable(name: str, value: int):
+    """``pa_set_tunable`` + a host-side record (the mirror needs to know whether the
+    staged methods run over this library's own NVLink copy kernels)."""
+    check(lib.pa_set_tunable(name.encode(), int(value)))
+    _tunables[name] = int(value)
+
+
 class _Plan:
     """Owner of one ``pa_plan`` handle (geometry + launch descriptors + streams)."""
 
@@ -77,10 +87,15 @@ class _Plan:
         info = PlanInfo()
         check(lib.pa_plan_get_info(h, C.byref(info)))
         self.info = info
+        self._ipc_handles = []   # every pa_ipc_import this plan holds a reference for
+        self._windows = {}       # key -> registered local pointer
+        self._arena_ptr = None   # recv_buf the peers' arena windows were registered against
 
     def __del__(self):
         try:
-            lib.pa_plan_destroy(self.h)
+            lib.pa_plan_destroy(self.h)  # (synchronises nothing: the mappings go after it)
+            for hh in self._ipc_handles:
+                lib.pa_ipc_release(hh)
         except Exception:
             pass
 
@@ -120,46 +135,48 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
-    """Collective: expose ``Ao``'s device buffer to the peers of the grid line and
-    map theirs (``pa_ipc_export`` / ``pa_ipc_import`` / ``pa_plan_set_window``).
-    Cached per destination array; SPMD programs hit or miss the cache together."""
-    import weakref
+def _exchange_windows(plan: _Plan, key, ptr: int, comm, setter):
+    """Collective over the communicator (like ``MPI_Win_create``): expose the device
+    allocation at ``ptr`` (0: this rank owns nothing -- it exports nothing but still
+    maps its peers') to the peers of the plan's grid line, map theirs and hand each
+    mapped pointer to ``setter(n, mapped)``.
+
+    Whether anything has to be (re)mapped is decided COLLECTIVELY: a rank whose own
+    pointer is unchanged still takes part when a peer re-allocated its array.
+    Failures never leave ranks stuck in a collective: all raise together."""
     import torch.distributed as dist
 
-    lo, hi = Ao.data_ptr(), Ao.data_ptr() + Ao.data.numel() * Ao.elsize
-    si, ei = Ai.data_ptr(), Ai.data_ptr() + Ai.data.numel() * Ai.elsize
-    if lo < ei and si < hi:
-        return  # aliased (in-place): libpa_b200 takes the staged schedule, no window needed
-    reg = plan.__dict__.setdefault("_windows", {})
-    ent = reg.get(id(Ao))
-    if ent is not None and ent[0]() is Ao and ent[1] == lo:
-        return
     if not dist.is_initialized():
-        raise ArgumentError(_lib.PA_EINVAL, "PeerPut needs torch.distributed for the handle exchange")
+        raise ArgumentError(_lib.PA_EINVAL, "one-sided / peer-memory transposes need "
+                            "torch.distributed for the handle exchange")
     _stream_ptr()  # binds the library to torch's current device
+    changed = plan._windows.get(key) != ptr
     h = C.create_string_buffer(_lib.PA_IPC_HANDLE_BYTES)
     off = C.c_int64()
-    # failures must not leave the other ranks stuck in the collectives below:
-    # every rank always takes part in both exchanges and all raise together
     err = None
-    st = lib.pa_ipc_export(C.c_void_p(lo), h, C.byref(off))
-    if st != _lib.PA_OK:
-        err = f"rank {comm.rank}: export failed: {lib.pa_last_error().decode()}"
+    if ptr:
+        st = lib.pa_ipc_export(C.c_void_p(ptr), h, C.byref(off))
+        if st != _lib.PA_OK:
+            err = f"rank {comm.rank}: export failed: {lib.pa_last_error().decode()}"
     allh = [None] * comm.size
-    dist.all_gather_object(allh, (comm.rank, bytes(h.raw), off.value, err))
-    errs = [e for (_, _, _, e) in allh if e]
+    dist.all_gather_object(allh, (comm.rank, bytes(h.raw) if ptr else None, off.value, err, changed))
+    errs = [e for (_, _, _, e, _) in allh if e]
+    if not errs and not any(c for (_, _, _, _, c) in allh):
+        return  # every rank still holds current mappings
     if not errs:
-        byrank = {r: (hh, oo) for (r, hh, oo, _) in allh}
+        byrank = {r: (hh, oo) for (r, hh, oo, _, _) in allh}
         for n in range(1, plan.info.nproc + 1):
             peer = plan.peer(n)
             if peer.is_self:
                 continue
             hh, oo = byrank[peer.world_rank]
+            if hh is None:
+                continue  # that rank owns nothing: nothing will be put to / got from it
             mapped = C.c_void_p()
             st = lib.pa_ipc_import(hh, oo, C.byref(mapped))
             if st == _lib.PA_OK:
-                st = lib.pa_plan_set_window(plan.h, C.c_void_p(lo), n, mapped)
+                plan._ipc_handles.append(hh)
+                st = setter(n, mapped)
             if st != _lib.PA_OK:
                 err = f"rank {comm.rank}: import from rank {peer.world_rank} failed: " \
                       f"{lib.pa_last_error().decode()}"
@@ -168,8 +185,55 @@ def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
     dist.all_gather_object(oks, err)
     errs += [e for e in oks if e]
     if errs:
-        raise _lib.DeviceError(_lib.PA_ECUDA, "one-sided window setup failed: " + "; ".join(errs[:3]))
-    reg[id(Ao)] = (weakref.ref(Ao), lo)
+        raise _lib.DeviceError(_lib.PA_ECUDA, "peer window setup failed: " + "; ".join(errs[:3]))
+    plan._windows[key] = ptr
+
+
+def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
+    """Window of a one-sided method on ``Ao`` (``dest`` for PeerPut, ``src`` for
+    PeerGet): ``pa_ipc_export`` / ``pa_ipc_import`` / ``pa_plan_set_window``."""
+    lo, hi = Ao.data_ptr(), Ao.data_ptr() + Ao.data.numel() * Ao.elsize
+    si, ei = Ai.data_ptr(), Ai.data_ptr() + Ai.data.numel() * Ai.elsize
+    aliased = (lo < ei and si < hi) or (lo != 0 and lo == si)  # same rule as libpa_b200
+    if aliased:
+        # in place: libpa_b200 takes the staged schedule.  (Aliasing is a property of the
+        # ManyPencilArray, the same on every rank, so skipping the collective is symmetric.)
+        return _register_arenas(plan, Ao.pencil if plan.info.method == _lib.PA_PEER_PUT
+                                else Ai.pencil, comm)
+    ptr = lo if Ao.data.numel() > 0 else 0
+    _register_window_ptr(plan, ptr, comm)
+
+
+def _register_window_ptr(plan: _Plan, ptr: int, comm):
+    _exchange_windows(plan, ("win", ptr), ptr, comm,
+                      lambda n, mapped: lib.pa_plan_set_window(plan.h, C.c_void_p(ptr), n, mapped))
+
+
+def _uses_ipc_exchange(comm) -> bool:
+    return comm.transport == "ipc" or bool(_tunables.get("ipc_exchange"))
+
+
+def _register_arenas(plan: _Plan, Po: Pencil, comm):
+    """Own-kernel exchange of the staged methods: reserve the arenas at the maximum
+    size over the ranks (so that every rank re-allocates -- or not -- at the same
+    call), then expose ``recv_buf`` to the peers (``pa_plan_set_recv_window``)."""
+    import torch.distributed as dist
+
+    if plan.info.dim == 0 or plan.info.nproc == 1 or not _uses_ipc_exchange(comm):
+        return
+    _stream_ptr()
+    sizes = [None] * comm.size
+    dist.all_gather_object(sizes, (plan.info.send_bytes, plan.info.recv_bytes))
+    check(lib.pa_pencil_reserve(Po._h, max(1, max(s for s, _ in sizes)),
+                                max(1, max(r for _, r in sizes))))
+    fam = Po._family
+    plans = fam.__dict__.setdefault("_ipc_plans", [])
+    if not any(p is plan for p in plans):
+        plans.append(plan)
+    _, _, rp, _ = Po.buffers()
+    for pl in plans:  # every plan sharing these arenas (same list, same order on every rank)
+        _exchange_windows(pl, "arena", rp, comm,
+                          lambda n, mapped, pl=pl: lib.pa_plan_set_recv_window(pl.h, n, mapped))
 
 
 class Transposition:
@@ -191,11 +255,14 @@ class Transposition:
         self._plan = _get_plan(Pi, Po, Ai.extra_dims, Ai.elsize, method)  # remaining checks in C
         d = self._plan.info.dim
         self.dim = None if d == 0 else d  # :110
-        if d != 0 and self._plan.info.nproc > 1:
+        if d != 0 and self._plan.info.nproc > 1 and Pi.topology.comm.handle is not None:
+            comm = Pi.topology.comm
             if isinstance(method, PeerPut):
-                _register_window(self._plan, Ao, Ai, Pi.topology.comm)
+                _register_window(self._plan, Ao, Ai, comm)
             elif isinstance(method, PeerGet):
-                _register_window(self._plan, Ai, Ao, Pi.topology.comm)
+                _register_window(self._plan, Ai, Ao, comm)
+            else:
+                _register_arenas(self._plan, Po, comm)
 
     @property
     def plan(self) -> _Plan:
@@ -231,9 +298,87 @@ def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False)
     flags = (_lib.PA_WAITALL if waitall else 0) | (0 if overlap else _lib.PA_NO_OVERLAP) | (
         _lib.PA_STAGE_SELF if stage_self else 0)
     comm = t.Pi.topology.comm.handle
-    check(lib.pa_transpose(t.plan.h, comm, C.c_void_p(t.Ai.data_ptr()),
-                           C.c_void_p(t.Ao.data_ptr()), flags, _stream_ptr()))
+    # (an empty local array may have a null data pointer: the library accepts that)
+    check(lib.pa_transpose(t.plan.h, comm, C.c_void_p(t.Ai.data_ptr() or None),
+                           C.c_void_p(t.Ao.data_ptr() or None), flags, _stream_ptr()))
     return t if len(args) == 1 else args[0]
 
 
 transpose_bang = transpose_
+
+
+def transpose_host_(t: Transposition, host_src: torch.Tensor, host_dst: torch.Tensor):
+    """``transpose!`` on HOST arrays through ``pa_transpose_host``: upload, kernels and
+    download pipelined inside the library; returns when ``host_dst`` is valid.  Pin the
+    tensors (``pin_memory()``) for full PCIe bandwidth."""
+    _stream_ptr()
+    n_in, n_out = t.plan.info.length_in * t.Ai.elsize, t.plan.info.length_out * t.Ao.elsize
+    if host_src.numel() * host_src.element_size() != n_in or \
+            host_dst.numel() * host_dst.element_size() != n_out or \
+            host_src.is_cuda or host_dst.is_cuda or \
+            not host_src.is_contiguous() or not host_dst.is_contiguous():
+        raise _lib.DimensionMismatch(_lib.PA_EDIM, "host arrays must be dense CPU tensors of the "
+                                     "local array sizes")
+    check(lib.pa_transpose_host(t.plan.h, t.Pi.topology.comm.handle,
+                                C.c_void_p(host_src.data_ptr() if n_in else None),
+                                C.c_void_p(host_dst.data_ptr() if n_out else None), 0))
+    return host_dst
+
+
+class HostChain:
+    """A sequence of transpositions applied to host arrays (``pa_host_chain_*``): what a
+    PencilFFTs-style plan over ``Array``-backed pencils does around its transposes.
+
+        chain = HostChain([t_xy, t_yz, t_zy, t_yx])
+        k = chain.submit(hin, hout)      # asynchronous, double-buffered on the device
+        chain.wait(k)                    # hout valid
+
+    Only the pencils / methods of the transpositions are used; the device buffers belong
+    to the chain (for one-sided methods their windows are registered here, collectively).
+    """
+
+    def __init__(self, transpositions):
+        ts = list(transpositions)
+        self.ts = ts
+        n = len(ts)
+        arr = (C.c_void_p * n)(*[t.plan.h.value for t in ts])
+        comm = ts[0].Pi.topology.comm
+        h = C.c_void_p()
+        _stream_ptr()
+        check(lib.pa_host_chain_create(n, arr, comm.handle, C.byref(h)))
+        self.h = h
+        for slot in range(2):
+            for i, t in enumerate(ts):
+                info = t.plan.info
+                if info.dim == 0 or info.nproc == 1 or comm.handle is None:
+                    continue
+                if info.method in (_lib.PA_PEER_PUT, _lib.PA_PEER_GET):
+                    which = (1 - i % 2) if info.method == _lib.PA_PEER_PUT else (i % 2)
+                    p = C.c_void_p()
+                    check(lib.pa_host_chain_buffer(h, slot, which, C.byref(p), None))
+                    _register_window_ptr(t.plan, p.value, comm)
+                else:
+                    _register_arenas(t.plan, t.Po, comm)
+
+    def submit(self, host_src: torch.Tensor, host_dst: torch.Tensor) -> int:
+        k = C.c_int64()
+        check(lib.pa_host_chain_submit(self.h, C.c_void_p(host_src.data_ptr()),
+                                       C.c_void_p(host_dst.data_ptr()), C.byref(k)))
+        return k.value
+
+    def wait(self, ticket: int = -1):
+        check(lib.pa_host_chain_wait(self.h, ticket))
+
+    def time_begin(self):
+        check(lib.pa_host_chain_time_begin(self.h))
+
+    def time_end(self) -> float:
+        ms = C.c_float()
+        check(lib.pa_host_chain_time_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib.pa_host_chain_destroy(self.h)
+        except Exception:
+            pass

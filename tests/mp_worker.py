@@ -1,6 +1,11 @@
 """Worker for the multi-process tests; launched with torch.distributed.run.
 
   mode "nccl": real path -- pa.transpose_ over NCCL, one GPU per rank;
+  mode "ipc":  real path with the NCCL-free communicator (CUDA-IPC windows + flag
+               words only): the ranks may SHARE one GPU, so a single-GPU box runs
+               the whole multi-rank schedule -- one-sided puts/gets, the staged
+               PointToPoint / Alltoallv schedules over the library's own copy
+               kernels, waitall=false + Waitall, in-place fallback, empty blocks;
   mode "gloo": CPU box -- the C planner's descriptors are interpreted with
                NumPy (tests/util.apply_block) and the exchange follows the
                plan's peer table over gloo send/recv.  Checks the N>1 host
@@ -66,7 +71,10 @@ def gloo_transpose(plan, src, dtype, it, rank):
 def main():
     mode = sys.argv[1]
     if mode == "nccl":
-        comm = pa.comm_world()
+        comm = pa.comm_world(transport="nccl")
+    elif mode == "ipc":
+        comm = pa.comm_world(transport="ipc")
+        assert comm.transport == "ipc" and comm.handle is not None
     else:
         dist.init_process_group("gloo")
         comm = pa.Comm(dist.get_rank(), dist.get_world_size())
@@ -86,10 +94,20 @@ def main():
                         pa.Pencil(pens[0], decomp_dims=d, permute=perm_of(p)))
         g = O.global_pattern(case["dims"], extra, it)
         cur_o = O.scatter(g, opens[0], extra, dtype)
-        variants = [(pa.PointToPoint(), True, True), (pa.PointToPoint(), False, True),
-                    (pa.Alltoallv(), True, True), (pa.PointToPoint(), True, False),
-                    (pa.PeerPut(), True, True), (pa.PeerGet(), True, True),
-                    (pa.PeerGet(), True, False)]
+        # (method, overlap, waitall, tunables)
+        variants = [(pa.PointToPoint(), True, True, {}), (pa.PointToPoint(), False, True, {}),
+                    (pa.Alltoallv(), True, True, {}), (pa.PointToPoint(), True, False, {}),
+                    (pa.PeerPut(), True, True, {}), (pa.PeerGet(), True, True, {}),
+                    (pa.PeerGet(), True, False, {}),
+                    (pa.PointToPoint(), True, True, {"p2p_chunks": 3}),
+                    (pa.PointToPoint(), False, False, {"p2p_chunks": 2, "staged_ctas": 8}),
+                    (pa.PeerPut(), True, True, {"multi_put": 0}),
+                    (pa.PeerGet(), True, False, {"multi_put": 0}),
+                    (pa.Alltoallv(), True, True, {"multi_put": 0})]
+        if mode == "nccl":  # the own-kernel exchange beside NCCL on the same communicator
+            variants += [(pa.PointToPoint(), True, True, {"ipc_exchange": 1}),
+                         (pa.Alltoallv(), True, True, {"ipc_exchange": 1, "p2p_chunks": 2})]
+        defaults = {"p2p_chunks": 1, "staged_ctas": 0, "multi_put": 1, "ipc_exchange": 0}
         if mode == "gloo":
             cur = cur_o[rank].data.reshape(-1, order="F").copy()
         else:
@@ -97,6 +115,7 @@ def main():
             cur = pa.PencilArray.undef(tdt, pens[0], *extra)
             cur.data.view(torch.uint8).reshape(-1).copy_(torch.from_numpy(
                 np.ascontiguousarray(cur_o[rank].data.reshape(-1, order="F")).view(np.uint8).copy()))
+            torch.cuda.synchronize()
         for k in range(1, len(case["chain"])):
             nxt_o = [O.OArray.undef(dtype, po, *extra) for po in opens[k]]
             O.transpose_all(nxt_o, cur_o)
@@ -108,7 +127,9 @@ def main():
                 cur = got
             else:
                 nxt = None
-                for (method, overlap, waitall) in variants:
+                for (method, overlap, waitall, tun) in variants:
+                    for name, v in {**defaults, **tun}.items():
+                        pa.set_tunable(name, v)
                     nxt = pa.PencilArray.undef(tdt, pens[k], *extra)
                     nxt.data.view(torch.uint8).fill_(0x5A)
                     t = pa.Transposition(nxt, cur, method=method)
@@ -118,10 +139,12 @@ def main():
                     torch.cuda.synchronize()
                     got = nxt.data.view(torch.uint8).reshape(-1).cpu().numpy()
                     assert got.tobytes() == want.view(np.uint8).tobytes(), \
-                        (case["name"], k, rank, method, overlap, waitall)
+                        (case["name"], k, rank, method, overlap, waitall, tun)
+                for name, v in defaults.items():
+                    pa.set_tunable(name, v)
                 cur = nxt
             cur_o = nxt_o
-        if mode == "nccl" and len(case["chain"]) >= 3 and not extra:
+        if mode != "gloo" and len(case["chain"]) >= 3 and not extra:
             # in place: ManyPencilArray over the first three pencils (test/pencils.jl:224-239)
             A = pa.ManyPencilArray(tdt, *pens[:3])
             o0 = O.scatter(g, opens[0], extra, dtype)
@@ -148,4 +171,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        tb = traceback.format_exc()
+        sys.stderr.write("".join(f"WORKER-ERROR[{os.environ.get('RANK', '?')}] {l}\n"
+                                 for l in tb.splitlines()))
+        sys.stderr.flush()
+        os._exit(1)

@@ -164,3 +164,68 @@ def test_non_power_of_two_element_sizes(itemsize):
             want = np.ascontiguousarray(a.data.reshape(-1, order="F")).view(np.uint8)
             assert nxt[r].view(np.uint8)[:want.size].tobytes() == want.tobytes(), (k, r)
         cur_o = nxt_o
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if math.prod(c["grid"]) > 1][:10],
+                         ids=[c["name"] for c in CASES if math.prod(c["grid"]) > 1][:10])
+@pytest.mark.parametrize("nparts", [1, 2, 3, 7])
+def test_chunked_blocks_tile_the_wire_layout(case, nparts):
+    """The chunked PointToPoint schedule (tunable p2p_chunks): the pack chunks of a
+    block, run one after the other, fill exactly the bytes the whole pack fills; each
+    chunk is ONE contiguous piece of the wire block; the receiver cuts its unpack at
+    the same wire offsets (sender and receiver never talk about the cuts)."""
+    import ctypes as C
+    from pencilarrays_b200._lib import lib, check, BlockDesc
+    from util import apply_block
+    dtype, it, extra = DTYPES[case["it"]], case["it"], case["extra"]
+    ranks, steps = build_chain(case)
+    g = O.global_pattern(case["dims"], extra, it)
+    cur_o = O.scatter(g, [po for (_, po) in steps[0]], extra, dtype)
+    for k in range(1, min(3, len(steps))):
+        nxt_o = [O.OArray.undef(dtype, po, *extra) for (_, po) in steps[k]]
+        states = O.transpose_all(nxt_o, cur_o, keep_states=True)
+        plans = [_Plan(steps[k - 1][r][0], steps[k][r][0], extra, it, pa.PointToPoint())
+                 for r in range(len(ranks))]
+        if plans[0].info.dim != 0:
+            for r, pl in enumerate(plans):
+                src = cur_o[r].data.reshape(-1, order="F").copy()
+                send = np.zeros(max(1, pl.info.send_bytes // it), dtype=dtype)
+                recv = states[r].recv_buf.copy()
+                dst = np.zeros(max(1, pl.info.length_out), dtype=dtype)
+                for p in range(1, pl.info.nproc + 1):
+                    peer = pl.peer(p)
+                    if peer.is_self:
+                        apply_block(pl.block(1, p), recv, dst)
+                        continue
+                    end_s, end_r = peer.send_offset, peer.recv_offset
+                    for c in range(nparts):
+                        d, off, nb = BlockDesc(), C.c_int64(), C.c_int64()
+                        check(lib.pa_plan_get_chunk(pl.h, 0, p, c, nparts, C.byref(d), C.byref(off),
+                                                    C.byref(nb)))
+                        if nb.value:
+                            assert off.value == end_s  # contiguous, in order
+                        end_s += nb.value
+                        apply_block(d, src, send)
+                        d2, off2, nb2 = BlockDesc(), C.c_int64(), C.c_int64()
+                        check(lib.pa_plan_get_chunk(pl.h, 1, p, c, nparts, C.byref(d2), C.byref(off2),
+                                                    C.byref(nb2)))
+                        if nb2.value:
+                            assert off2.value == end_r
+                        end_r += nb2.value
+                        apply_block(d2, recv, dst)
+                        # the matching chunk on the sending side of this receive has the same size
+                        q = peer.world_rank
+                        back = [pp for pp in range(1, pl.info.nproc + 1)
+                                if plans[q].peer(pp).world_rank == pl.peer(pl.info.self_index).world_rank][0]
+                        d3, off3, nb3 = BlockDesc(), C.c_int64(), C.c_int64()
+                        check(lib.pa_plan_get_chunk(plans[q].h, 0, back, c, nparts, C.byref(d3),
+                                                    C.byref(off3), C.byref(nb3)))
+                        assert nb3.value == nb2.value
+                        # ... and that sender aims at exactly this receive slot of mine
+                        assert plans[q].peer(back).remote_recv_offset == peer.recv_offset
+                    assert end_s == peer.send_offset + peer.send_count
+                    assert end_r == peer.recv_offset + peer.recv_count
+                ns = pl.info.send_bytes // it
+                assert beq(send[:ns], states[r].send_buf[:ns])
+                assert beq(dst[:nxt_o[r].data.size], nxt_o[r].data.reshape(-1, order="F"))
+        cur_o = nxt_o
