@@ -650,6 +650,7 @@ def run_b200(args):
         return perr if perr else bool(flag.item())
 
     placed = placement(ts)
+    ux.data.copy_(orig)
 
     # ---- the other methods beside it (N > 1): the schedules north_star names run over NCCL;
     # each gets warm-up, timed steps, round-trip and full-size placement checks in THIS run

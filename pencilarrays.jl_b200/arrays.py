@@ -49,6 +49,10 @@ class PencilArray:
         self.data = data
         self.extra_dims = extra_dims
         self.space_dims = _p_size_local(pencil, LogicalOrder())
+        # arrays carved out of one ManyPencilArray alias each other BY CONSTRUCTION, also on
+        # a rank where one of them is empty (every rank must then take the same schedule)
+        self._owner = None
+        self._base_ptr = 0
 
     @classmethod
     def undef(cls, dtype, pencil: Pencil, *extra_dims, device=None):
@@ -85,7 +89,8 @@ class PencilArray:
         return self.data.element_size()
 
     def data_ptr(self):
-        return self.data.data_ptr()
+        p = self.data.data_ptr()
+        return p if p else self._base_ptr  # an empty view still names its buffer
 
     def __len__(self):
         return self.data.numel()
@@ -137,7 +142,9 @@ class ManyPencilArray:
             mem = _p_size_local(p, MemoryOrder())
             cnt = math.prod(mem) * math.prod(extra_dims)
             view = self.data[:cnt].view(tuple(reversed(mem + extra_dims)))
-            self.arrays.append(PencilArray(p, view, extra_dims))
+            a = PencilArray(p, view, extra_dims)
+            a._owner, a._base_ptr = self, self.data.data_ptr()
+            self.arrays.append(a)
 
     def __getitem__(self, i):  # 1-based like A[1], A[2] of the reference
         if i < 1 or i > len(self.arrays):

@@ -58,14 +58,22 @@ struct KParams {
   int no;     // outer dims
   long long oe[MAXO], os[MAXO], od[MAXO];
   int lx_log2, ux_log2;  // rows thread/unroll shape
+  int y_fastest;         // tile order: consecutive CTAs walk along Y (destination rows) first
 };
 
 __device__ __forceinline__ void decode_tile(const KParams& p, ull bid, unsigned& tx, unsigned& ty,
                                             const char*& s, char*& d) {
-  tx = (unsigned)(bid % p.tiles_x);
-  bid /= p.tiles_x;
-  ty = (unsigned)(bid % p.tiles_y);
-  bid /= p.tiles_y;
+  if (p.y_fastest) {
+    ty = (unsigned)(bid % p.tiles_y);
+    bid /= p.tiles_y;
+    tx = (unsigned)(bid % p.tiles_x);
+    bid /= p.tiles_x;
+  } else {
+    tx = (unsigned)(bid % p.tiles_x);
+    bid /= p.tiles_x;
+    ty = (unsigned)(bid % p.tiles_y);
+    bid /= p.tiles_y;
+  }
   s = p.src;
   d = p.dst;
 #pragma unroll 1
@@ -359,23 +367,30 @@ struct TransBody {
       }
     }
     __syncthreads();
-    constexpr int IT = TA * TBQ / 256;
+    if constexpr (!DE) {
+      constexpr int IT = TA * TBQ / 256;
 #pragma unroll
-    for (int k = 0; k < IT; ++k) {
-      const int idx = threadIdx.x + 256 * k;
-      const int xr = idx / TBQ, qq = idx % TBQ;
-      const long long x = SE ? x0 + xr : x0 + (long long)(xr & 31) * V + (xr >> 5);
-      const long long y = y0 + (long long)qq * V;
-      if constexpr (!DE) {
+      for (int k = 0; k < IT; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int xr = idx / TBQ, qq = idx % TBQ;
+        const long long x = SE ? x0 + xr : x0 + (long long)(xr & 31) * V + (xr >> 5);
+        const long long y = y0 + (long long)qq * V;
         if (x < p.ex && y < p.ey) st_stream<uint4>(d + x * p.sx_d + y * S, sm[xr * PITCH + qq]);
-      } else {
-        if (x < p.ex && y < p.ey) {
-          ET e[V];
-          unpack_item(sm[xr * PITCH + qq], e);
-#pragma unroll
-          for (int j = 0; j < V; ++j)
-            if (y + j < p.ey) st_stream<ET>(d + x * p.sx_d + (y + j) * S, e[j]);
-        }
+      }
+    } else {
+      // element stores (the destination rows are only S-byte aligned): consecutive lanes
+      // take consecutive ELEMENTS of a destination row -- shared memory read as S-byte
+      // words of the 16-byte items, conflict-free, 32 x S bytes contiguous per warp store
+      const ET* sme = reinterpret_cast<const ET*>(sm);
+      constexpr int ITE = TA * TB / 256;
+#pragma unroll 8
+      for (int k = 0; k < ITE; ++k) {
+        const int idx = threadIdx.x + 256 * k;
+        const int xr = idx / TB, ye = idx % TB;
+        const long long x = SE ? x0 + xr : x0 + (long long)(xr & 31) * V + (xr >> 5);
+        const long long y = y0 + ye;
+        if (x < p.ex && y < p.ey)
+          st_stream<ET>(d + x * p.sx_d + y * S, sme[(xr * PITCH + ye / V) * V + (ye % V)]);
       }
     }
   }
@@ -692,17 +707,26 @@ static pa_status prepare(const BlockCopy& b, const void* src, void* dst, KParams
     sel.w = W;
     if (vec_used) *vec_used = W;
   } else if (b.klass == KC_TRANSPOSE && (S == 4 || S == 8 || S == 16)) {
-    // destination-run length TBQ*16 B: 512 B by default; 256 B for small blocks
-    // (more, smaller tiles -> shorter tail), tunable "transpose_tbq" overrides
-    int tbq = g_tun.transpose_tbq;
-    if (tbq != 16 && tbq != 32) tbq = (b.count * S < g_tun.small_block_bytes) ? 16 : 32;
-    if (S == 4) tbq = 16;
+    // destination-run length of a tile = TBQ*16 B.  256 B (TBQ = 16) wins or ties on every
+    // shape measured on B200, from 128 MiB to 2 GiB blocks (profiles/r2_shapes_sweep.txt:
+    // more, smaller tiles -> shorter tail, fewer DRAM pages open per tile); tunable
+    // "transpose_tbq" = 32 selects 512-B runs
+    int tbq = g_tun.transpose_tbq == 32 && S != 4 ? 32 : 16;
     const int V = 16 / (int)S;
     p.tiles_x = (unsigned)cdiv(X.e, 32 * V);
     p.tiles_y = (unsigned)cdiv(Y.e, tbq * V);
     sel.fam = F_TRANS;
     sel.w = (int)S;
     sel.tbq = tbq;
+    // Tile order.  Consecutive CTAs should complete the SHORT rows first: when the
+    // destination rows are much shorter than the source rows (few tiles along Y, many
+    // along X -- typically a 2-d transpose left after merging dims) walking along Y
+    // first fills whole destination rows (full DRAM pages) instead of 256-byte pieces
+    // of thousands of them; measured 0.45-0.74 -> 0.95-0.99 of the HBM roofline on the
+    // r2c-shaped grids, neutral elsewhere (profiles/r2_shapes_sweep.txt).  Tunable
+    // "transpose_y_fastest": -1 = this rule (default), 0 / 1 = forced.
+    p.y_fastest = g_tun.transpose_y_fastest >= 0 ? g_tun.transpose_y_fastest
+                                                 : (2ull * p.tiles_y <= (unsigned long long)p.tiles_x);
     sel.se = S < 16 && sal < 16;
     sel.de = S < 16 && dal < 16;
     if (vec_used) *vec_used = (sel.se || sel.de) ? (int)S : 16;

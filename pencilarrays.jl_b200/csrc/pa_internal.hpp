@@ -153,10 +153,11 @@ struct Tunables {
   int remote_ctas = -4;   // grid cap of put/get kernels: n > 0 CTAs, n < 0 = |n| per SM, 0 = uncapped
                           // (4 per SM: full NVLink rate in profiles/r1_nvlink_microbench.txt)
   int box_copy_ctas = 0;  // grid cap applied to pa_box_copy (benchmarks)
-  int transpose_tbq = 0;  // 0 = auto; 16 / 32 = 16-byte items per destination run of a transpose tile
-  // blocks below this size use TBQ = 16: 256^3 Float64 permutes go from 76 % to 94 % of the HBM
-  // roofline, 1-2 GiB blocks are indifferent (profiles/r1_tile_sweep.txt)
-  long long small_block_bytes = 256ll << 20;
+  int transpose_y_fastest = -1;  // transpose tile order: 1 = consecutive CTAs along the destination rows,
+                                 // 0 = along the source rows, -1 = along the side with fewer tiles (kernels.cu)
+  int transpose_tbq = 0;  // 16-byte items per destination run of a transpose tile: 0 / 16 = 256-byte runs
+                          // (default: best or tied on every measured shape), 32 = 512-byte runs
+  long long small_block_bytes = 256ll << 20;  // (kept for ABI compatibility of pa_set_tunable; unused)
   int bulk_rows = 0;     // 1: row copies run as the TMA bulk-copy pipeline (k_rows_bulk)
   int nccl_register = 1;  // staging arenas from ncclMemAlloc + ncclCommRegister (registered NCCL p2p:
                           // exchange 637 -> 673 GB/s at N=2); falls back to cudaMalloc when unavailable

@@ -630,10 +630,11 @@ pa_status permute_local(Plan* P, const void* src, void* dst, void* scratch, void
 }
 
 // one dense run of `bytes` as a box copy (the IPC transport's block mover)
-static BlockCopy contiguous_block(i64 bytes) {
+static BlockCopy contiguous_block(i64 bytes, const void* src, const void* dst) {
   BlockCopy b;
   int w = 16;
-  while (w > 1 && bytes % w) w /= 2;
+  const uintptr_t bits = (uintptr_t)bytes | (uintptr_t)src | (uintptr_t)dst;
+  while (w > 1 && bits % w) w /= 2;
   b.elsize = w;
   b.nd_raw = 1;
   b.raw[0] = Dim{bytes / w, 1, 1};
@@ -893,7 +894,7 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
     if (sl <= 0) return PA_OK;
     const Peer& pt = P->peers[to];
     char* rdst = (char*)P->recv_windows[to] + pt.remote_recv_off * ES + (so - pt.send_off * ES);
-    return launch_block(contiguous_block(sl), sbuf + so, rdst, S.comm_s, nullptr,
+    return launch_block(contiguous_block(sl, sbuf + so, rdst), sbuf + so, rdst, S.comm_s, nullptr,
                         g_tun.remote_ctas);
   };
   auto data_signal = [&](int to) -> pa_status {
@@ -962,9 +963,10 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
         send_range(to_of[k], 0, &so, &sl);
         if (sl <= 0) continue;
         const Peer& pt = P->peers[to_of[k]];
-        cb.push_back(contiguous_block(sl));
+        char* rdst = (char*)P->recv_windows[to_of[k]] + pt.remote_recv_off * ES;
+        cb.push_back(contiguous_block(sl, sbuf + so, rdst));
         ss.push_back(sbuf + so);
-        dd.push_back((char*)P->recv_windows[to_of[k]] + pt.remote_recv_off * ES);
+        dd.push_back(rdst);
       }
       for (auto& b : cb) bp.push_back(&b);
       pa_status rc = PA_EINCOMPAT;

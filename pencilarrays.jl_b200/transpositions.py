@@ -194,7 +194,10 @@ def _register_window(plan: _Plan, Ao: PencilArray, Ai: PencilArray, comm):
     PeerGet): ``pa_ipc_export`` / ``pa_ipc_import`` / ``pa_plan_set_window``."""
     lo, hi = Ao.data_ptr(), Ao.data_ptr() + Ao.data.numel() * Ao.elsize
     si, ei = Ai.data_ptr(), Ai.data_ptr() + Ai.data.numel() * Ai.elsize
-    aliased = (lo < ei and si < hi) or (lo != 0 and lo == si)  # same rule as libpa_b200
+    # same rule as libpa_b200 (same base pointer, or overlapping ranges); views of one
+    # ManyPencilArray alias on every rank, empty ones included
+    aliased = (lo < ei and si < hi) or (lo != 0 and lo == si) or \
+        (Ao._owner is not None and Ao._owner is Ai._owner)
     if aliased:
         # in place: libpa_b200 takes the staged schedule.  (Aliasing is a property of the
         # ManyPencilArray, the same on every rank, so skipping the collective is symmetric.)
