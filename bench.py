@@ -492,6 +492,8 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: the transpose! path has no CPU fallback")
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local % torch.cuda.device_count())
+    if args.nccl_ctas:
+        pa.set_tunable("nccl_ctas", args.nccl_ctas)  # before the communicator exists
     comm = pa.comm_world() if n > 1 else pa.COMM_SELF
     rank = comm.rank
     W = WORKLOADS[args.workload]
@@ -566,9 +568,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    ovl = [overlap]
+
     def chain(tl, evs=None):
         for i, t in enumerate(tl):
-            pa.transpose_(t, waitall=True, overlap=overlap)
+            pa.transpose_(t, waitall=True, overlap=ovl[0])
             if evs is not None:
                 evs[i + 1].record()
 
@@ -658,16 +662,27 @@ def run_b200(args):
     if n > 1 and not args.only_default:
         others = {}
         variants = [("pointtopoint", {}), ("alltoallv", {}), ("peerget", {}),
-                    ("pointtopoint", {"p2p_chunks": 4}), ("pointtopoint", {"ipc_exchange": 1}),
+                    ("pointtopoint", {"overlap": 0}), ("pointtopoint", {"self_first": 1}),
+                    ("pointtopoint", {"p2p_chunks": 4}), ("pointtopoint", {"p2p_chunks": 8}),
+                    ("pointtopoint", {"p2p_chunks": 4, "staged_ctas": -2}),
+                    ("pointtopoint", {"p2p_chunks": 8, "staged_ctas": -1}),
+                    ("pointtopoint", {"ipc_exchange": 1}),
+                    ("pointtopoint", {"ipc_exchange": 1, "p2p_chunks": 4}),
+                    ("alltoallv", {"ipc_exchange": 1}),
                     ("peerput", {"multi_put": 0})]
+        if args.variants:
+            variants = [v for i, v in enumerate(variants) if str(i) in args.variants.split(",")]
         defaults = {"p2p_chunks": args.p2p_chunks or 1, "ipc_exchange": 1 if args.ipc_exchange else 0,
-                    "multi_put": 0 if args.no_multi_put else 1}
+                    "multi_put": 0 if args.no_multi_put else 1, "staged_ctas": args.staged_ctas or 0,
+                    "self_first": 0}
         for mname, tun in variants:
             label = mname + "".join(f" {k}={v}" for k, v in tun.items())
             if mname == name and not tun:
                 continue
             for k, v in {**defaults, **tun}.items():
-                pa.set_tunable(k, v)
+                if k != "overlap":
+                    pa.set_tunable(k, v)
+            ovl[0] = bool(tun.get("overlap", overlap))
             tl, msg = make_ts(mname)
             if tl is None:
                 others[label] = {"unavailable": msg[:160]}
@@ -685,6 +700,7 @@ def run_b200(args):
                                  "placement_exact_full_size": placement(tl)}
             for k, v in defaults.items():
                 pa.set_tunable(k, v)
+            ovl[0] = overlap
         ux.data.copy_(orig)
 
     # ---- per-kernel roofline -----------------------------------------------------------
@@ -805,8 +821,9 @@ def run_b200(args):
     # ---- exchange timing (N > 1): library CUDA-event sections, sequential phases ----
     sections = None
     if n > 1:
-        sections = {}
-        for lname, t in zip(LEGS[:2], ts[:2]):
+        sections = {"method": "PointToPoint, phases run strictly one after the other (PA_NO_OVERLAP)"}
+        sts, _ = make_ts("pointtopoint")
+        for lname, t in zip(LEGS[:2], sts or []):
             if t.dim is None:
                 continue
             t.enable_timing(True)
@@ -892,10 +909,12 @@ def main():
     ap.add_argument("--remote-ctas", type=int, default=None,
                     help="grid cap of the PeerPut/PeerGet kernels (tunable remote_ctas)")
     ap.add_argument("--p2p-chunks", type=int, default=None, help="tunable p2p_chunks")
+    ap.add_argument("--nccl-ctas", type=int, default=None, help="ncclCommInitRankConfig min/maxCTAs")
     ap.add_argument("--staged-ctas", type=int, default=None, help="tunable staged_ctas")
     ap.add_argument("--ipc-exchange", action="store_true", help="staged methods over own copy kernels")
     ap.add_argument("--no-multi-put", action="store_true", help="one launch per peer block")
     ap.add_argument("--only-default", action="store_true", help="N>1: skip the other methods")
+    ap.add_argument("--variants", default=None, help="N>1: comma-separated indices of the method variants to run")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (kernels, configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -62,6 +62,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   else if (!strcmp(name, "multi_put")) g_tun.multi_put = (int)value;
   else if (!strcmp(name, "p2p_chunks")) g_tun.p2p_chunks = (int)value;
   else if (!strcmp(name, "staged_ctas")) g_tun.staged_ctas = (int)value;
+  else if (!strcmp(name, "self_first")) g_tun.self_first = (int)value;
   else if (!strcmp(name, "ipc_exchange")) g_tun.ipc_exchange = (int)value;
   else if (!strcmp(name, "fence_timeout_ms")) g_tun.fence_timeout_ms = value;
   else if (!strcmp(name, "pdl")) g_tun.pdl = (int)value;

@@ -505,6 +505,7 @@ pa_status launch_flags(int n, ull* const* remote, ull* const* local, const ull* 
       fp.do_wait = wt;
       fp.timeout_ns = timeout_ns;
       fp.err = err;
+      cudaGetLastError();  // (clear: only this launch is being checked)
       k_flags<<<1, 64, 0, (cudaStream_t)stream>>>(fp);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) {
@@ -769,6 +770,7 @@ static pa_status launch_bulk(const BlockCopy& b, KParams& p, cudaStream_t st, in
   p.total = units;
   long long ctas = max_ctas > 0 ? max_ctas : (max_ctas < 0 ? -max_ctas : 3) * (long long)sm_count();
   if ((ull)ctas > units) ctas = (long long)units;
+  cudaGetLastError();
   k_rows_bulk<<<(unsigned)ctas, 32, BULK_STAGES * BULK_CHUNK, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return launch_err(e);
@@ -858,6 +860,7 @@ pa_status launch_multi(int nb, const BlockCopy* const* blocks, const void* const
   cudaStream_t st = (cudaStream_t)stream;
   return dispatch(sel0, [&](auto tag) -> pa_status {
     typedef typename decltype(tag)::Body B;
+    cudaGetLastError();
     k_multi<B><<<(unsigned)grid, 256, 0, st>>>(mp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return launch_err(e);

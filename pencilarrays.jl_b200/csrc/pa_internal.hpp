@@ -164,6 +164,7 @@ struct Tunables {
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
   int multi_put = 1;     // 1: one launch interleaving every peer's tiles (+ in-kernel flags) on the one-sided paths
   int p2p_chunks = 1;    // staged schedules: sub-blocks per peer block (pack-chunk -> send-chunk -> unpack-chunk)
+  int self_first = 0;    // staged schedules: 1 = self block first and beside the packs (round-1 order)
   int staged_ctas = 0;   // grid cap of pack/unpack kernels while an exchange is in flight (0 = uncapped, <0 per SM)
   int ipc_exchange = 0;  // 1: staged schedules move the blocks with this library's own NVLink copy kernels
                          //    (peer-mapped recv_buf + flag signals) even when an NCCL communicator exists

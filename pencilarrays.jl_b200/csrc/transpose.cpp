@@ -48,6 +48,7 @@ constexpr size_t IPC_BLOCK = 2u << 20;
   do {                                                                            \
     cudaError_t e_ = (call);                                                      \
     if (e_ != cudaSuccess) {                                                      \
+      cudaGetLastError(); /* do not leave it for an unrelated later check */      \
       set_error("%s failed: %s", #call, cudaGetErrorString(e_));                  \
       return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver)       \
                  ? PA_ENOGPU                                                      \
@@ -413,7 +414,11 @@ Buffers::~Buffers() {
 // grow-only, like resize! on the pencil's UInt8 vectors (Transpositions.jl:313-317)
 pa_status Buffers::reserve(i64 send_bytes, i64 recv_bytes) {
   auto grow = [this](void*& p, i64& cap, bool& from_nccl, i64 need) -> pa_status {
-    if (need <= cap) return PA_OK;
+    // (an arena from ncclMemAlloc is VMM memory: it cannot be exported with CUDA IPC,
+    //  so the own-kernel exchange replaces it by a plain allocation)
+    const bool wrong_kind = p && from_nccl && g_tun.ipc_exchange;
+    if (need <= cap && !wrong_kind) return PA_OK;
+    need = std::max(need, cap);
     // a previous exchange may still be reading/writing the old arena
     CU(cudaDeviceSynchronize());
     buffers_deregister(*this);
@@ -426,7 +431,7 @@ pa_status Buffers::reserve(i64 send_bytes, i64 recv_bytes) {
     from_nccl = false;
     // ncclMemAlloc only pays off (and NCCL is only touched at all) when an NCCL
     // communicator exists to register the arena with
-    if (g_tun.nccl_register && any_live_nccl() && nccl().ok && nccl().MemAlloc &&
+    if (g_tun.nccl_register && !g_tun.ipc_exchange && any_live_nccl() && nccl().ok && nccl().MemAlloc &&
         nccl().MemFree && nccl().MemAlloc(&p, (size_t)n) == ncclSuccess && p) {
       from_nccl = true;
     } else {
@@ -479,7 +484,7 @@ struct TransposeState {
   cudaStream_t pack_s = nullptr, comm_s = nullptr, unpack_s = nullptr;
   cudaStream_t host_s = nullptr, h2d_s = nullptr, d2h_s = nullptr;
   cudaEvent_t ev_start = nullptr, ev_allpacked = nullptr, ev_comm_done = nullptr,
-              ev_unpack_done = nullptr;
+              ev_unpack_done = nullptr, ev_self_done = nullptr;
   std::vector<cudaEvent_t> ev_packed, ev_recvd;  // [step * chunks + chunk]
   std::vector<cudaEvent_t> ev_host;              // host pipeline (per chunk: upload, kernel)
   bool timing = false;
@@ -498,7 +503,8 @@ void destroy_state(TransposeState* st) {
   if (!st) return;
   for (cudaStream_t s : {st->pack_s, st->comm_s, st->unpack_s, st->host_s, st->h2d_s, st->d2h_s})
     if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t e : {st->ev_start, st->ev_allpacked, st->ev_comm_done, st->ev_unpack_done})
+  for (cudaEvent_t e : {st->ev_start, st->ev_allpacked, st->ev_comm_done, st->ev_unpack_done,
+                        st->ev_self_done})
     if (e) cudaEventDestroy(e);
   for (auto e : st->ev_packed) cudaEventDestroy(e);
   for (auto e : st->ev_recvd) cudaEventDestroy(e);
@@ -531,7 +537,8 @@ static pa_status ensure_state(Plan* P) {
   CU(cudaStreamCreateWithFlags(&st->host_s, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&st->h2d_s, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&st->d2h_s, cudaStreamNonBlocking));
-  for (cudaEvent_t* e : {&st->ev_start, &st->ev_allpacked, &st->ev_comm_done, &st->ev_unpack_done})
+  for (cudaEvent_t* e : {&st->ev_start, &st->ev_allpacked, &st->ev_comm_done, &st->ev_unpack_done,
+                         &st->ev_self_done})
     CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   for (int i = 0; i < 7; ++i) CU(cudaEventCreate(&st->t[i]));
   CU(cudaMalloc((void**)&st->tok, 4 * (size_t)(P->nproc + 1)));
@@ -826,9 +833,15 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   }
 
   // ---- 1. pack ---------------------------------------------------------------
+  // The remote blocks go first and alone: the exchange is the critical path, every
+  // microsecond the first send waits for HBM is lost.  The self block follows on the
+  // same stream (fused K3: src -> dest in one pass) and fills the HBM time the
+  // NVLink-bound exchange leaves idle.  tunable "self_first" = 1 restores the
+  // reference's order (self block packed first, :393-403).
+  const bool self_first = stage_self || g_tun.self_first;
   if (stage_self) {
     RC(launch_block(self.pack, src, rbuf, S.pack_s, nullptr));  // tail of recv_buf (:393-403)
-  } else {
+  } else if (self_first) {
     RC(launch_block(P->self_fused, src, dst, S.unpack_s, nullptr));  // K3, one pass
   }
   for (int k = 1; k < nproc; ++k) {
@@ -840,6 +853,8 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   }
   CU(cudaEventRecord(S.ev_allpacked, S.pack_s));
   if (timing) CU(cudaEventRecord(S.t[1], S.pack_s));
+  if (!self_first) RC(launch_block(P->self_fused, src, dst, S.pack_s, nullptr, cap));
+  CU(cudaEventRecord(S.ev_self_done, S.pack_s));
 
   // ---- 2. exchange -------------------------------------------------------------
   const int np = nproc - 1;
@@ -1021,7 +1036,7 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   if (timing) CU(cudaEventRecord(S.t[5], S.unpack_s));
 
   // ---- join -----------------------------------------------------------------
-  CU(cudaStreamWaitEvent(user, S.ev_allpacked, 0));    // src may be reused by the caller
+  CU(cudaStreamWaitEvent(user, S.ev_self_done, 0));    // src may be reused by the caller
   CU(cudaStreamWaitEvent(user, S.ev_unpack_done, 0));  // dst complete
   S.sends_pending = true;
   S.pending_comm = comm;
