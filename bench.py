@@ -672,6 +672,10 @@ def run_b200(args):
                     ("peerput", {"multi_put": 0})]
         if args.variants:
             variants = [v for i, v in enumerate(variants) if str(i) in args.variants.split(",")]
+        elif not args.all_variants:
+            # (chunked NCCL sends cost ~0.1 ms per operation: 2-3x slower at N=8, measured in
+            #  profiles/r2_bench_n8.json -- kept out of the default run)
+            variants = [v for v in variants if "p2p_chunks" not in v[1] and "self_first" not in v[1]]
         defaults = {"p2p_chunks": args.p2p_chunks or 1, "ipc_exchange": 1 if args.ipc_exchange else 0,
                     "multi_put": 0 if args.no_multi_put else 1, "staged_ctas": args.staged_ctas or 0,
                     "self_first": 0}
@@ -914,6 +918,7 @@ def main():
     ap.add_argument("--ipc-exchange", action="store_true", help="staged methods over own copy kernels")
     ap.add_argument("--no-multi-put", action="store_true", help="one launch per peer block")
     ap.add_argument("--only-default", action="store_true", help="N>1: skip the other methods")
+    ap.add_argument("--all-variants", action="store_true", help="N>1: also the chunked / reordered variants")
     ap.add_argument("--variants", default=None, help="N>1: comma-separated indices of the method variants to run")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (kernels, configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
