@@ -69,6 +69,15 @@ typedef enum pa_method {
 #define PA_NO_OVERLAP 2u /* run pack -> exchange -> unpack strictly in sequence      */
 #define PA_STAGE_SELF 4u /* self block through recv_buf like the reference (:393-403)
                             instead of the fused src->dest kernel                    */
+/* Fused neighbour step: the unpack of ALL blocks and a 1-d complex FFT
+ * along the destination's contiguous dimension (the one that has just become local:
+ * the reason the pencil is permuted, docs/src/Pencils.md:210-214) run as ONE kernel --
+ * `dst` receives fft(transposed array) (forward: exp(-2*pi*i*jk/n); backward: the
+ * unnormalised inverse, as FFTW / PencilFFTs).  ComplexF64, power-of-two lines of
+ * 8..1024 points, staged methods or local transposes, src and dst not aliased;
+ * PA_EINVAL otherwise (transpose, then transform, separately).                       */
+#define PA_FFT_FORWARD  8u
+#define PA_FFT_BACKWARD 16u
 
 typedef struct pa_topology pa_topology; /* MPITopology   (MPITopologies.jl:72-119) */
 typedef struct pa_pencil pa_pencil;     /* Pencil        (Pencils.jl:151-272)      */

@@ -25,6 +25,8 @@ PA_IPC_HANDLE_BYTES = 64
 PA_WAITALL = 1
 PA_NO_OVERLAP = 2
 PA_STAGE_SELF = 4
+PA_FFT_FORWARD = 8
+PA_FFT_BACKWARD = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpa_b200.so")

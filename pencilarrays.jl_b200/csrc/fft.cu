@@ -1,0 +1,304 @@
+// Fused unpack + batched 1-d FFT.
+//
+// In a PencilFFTs-style transform every transposition is followed by a 1-d FFT
+// along the dimension that has just become local and -- thanks to the pencil's
+// permutation -- contiguous (/root/reference/docs/src/Pencils.md:210-214;
+// docs/src/Transpositions.md:7-9).  Unfused that is two HBM round trips: the
+// unpack (copy_permuted!, Transpositions.jl:585-664) writes the permuted array,
+// the FFT reads and rewrites it.  This kernel does both in one:
+//
+//   * a CTA owns C = 8 consecutive destination LINES (same outer coordinates,
+//     8 consecutive values of the source-contiguous dim);
+//   * it gathers them from EVERY block of the transposition -- the blocks the
+//     peers sent (dense in recv_buf, wire layout of :380-416) and the self block
+//     straight out of `src` -- with 128-byte (8 x ComplexF64) coalesced loads,
+//     writing them transposed into shared memory (padded: fft_core.hpp);
+//   * runs the mixed-radix (2/4/8) decimation-in-frequency passes in shared
+//     memory, butterflies in registers;
+//   * stores each transformed line with fully contiguous 128-bit stores.
+//
+// HBM traffic: 2 * s * n bytes for n elements, the same as the plain unpack.
+// ComplexF64 lines of 8 ... 1024 points (power of two); anything else is refused
+// (PA_EINVAL) and the caller transposes and transforms separately.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "fft_core.hpp"
+#include "pa_internal.hpp"
+
+namespace pa {
+
+using pa_fft::cplx;
+
+constexpr int FFT_C = 8;      // lines per CTA
+constexpr int FFT_MAXB = 8;   // blocks gathered by one launch (ranks of a grid line on one box)
+constexpr int FFT_MAXO = PA_MAX_DIMS - 2;
+constexpr int FFT_THREADS = 256;
+
+struct FftBlock {
+  const char* src;  // block origin
+  int y0, ey;       // destination line range [y0, y0 + ey) this block fills
+  long long ssy;    // source byte stride of the line dim
+  long long so[FFT_MAXO];
+};
+struct FftParams {
+  int nb;
+  FftBlock blk[FFT_MAXB];
+  char* dst;
+  long long ex;   // columns (source-contiguous dim)
+  long long dsx;  // destination byte stride of a column step (= one line)
+  int no;
+  long long oe[FFT_MAXO], dso[FFT_MAXO];
+  int L, logL, sign, pitch;
+  const cplx* tw;
+  unsigned tiles_x;
+};
+
+struct SmLine {
+  cplx* p;
+  __device__ __forceinline__ cplx get(int i) const { return p[pa_fft::pad_index(i)]; }
+  __device__ __forceinline__ void put(int i, cplx v) { p[pa_fft::pad_index(i)] = v; }
+};
+
+__global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constant__ FftParams p) {
+  extern __shared__ __align__(16) unsigned char fft_smem[];
+  cplx* sm = reinterpret_cast<cplx*>(fft_smem);
+  const int t = threadIdx.x;
+  unsigned long long bid = blockIdx.x;
+  const long long x0 = (long long)(bid % p.tiles_x) * FFT_C;
+  bid /= p.tiles_x;
+  long long ok[FFT_MAXO];
+#pragma unroll 1
+  for (int i = 0; i < p.no; ++i) {
+    ok[i] = (long long)(bid % (unsigned long long)p.oe[i]);
+    bid /= (unsigned long long)p.oe[i];
+  }
+  const int ncol = (int)((p.ex - x0) < FFT_C ? (p.ex - x0) : FFT_C);
+
+  // ---- gather: 8 threads read 8 consecutive columns (128 B) of one source row ----
+  {
+    const int c = t % FFT_C, r = t / FFT_C;  // 32 rows per sweep
+    constexpr int RS = FFT_THREADS / FFT_C;
+    cplx* line = sm + c * p.pitch;
+#pragma unroll 1
+    for (int b = 0; b < p.nb; ++b) {
+      const FftBlock& B = p.blk[b];
+      const char* s = B.src + (x0 + c) * (long long)sizeof(cplx);
+#pragma unroll 1
+      for (int i = 0; i < p.no; ++i) s += ok[i] * B.so[i];
+      for (int y = r; y < B.ey; y += 4 * RS) {
+        double2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int yy = y + k * RS;
+          if (c < ncol && yy < B.ey)
+            v[k] = __ldcs(reinterpret_cast<const double2*>(s + (long long)yy * B.ssy));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int yy = y + k * RS;
+          if (c < ncol && yy < B.ey) line[pa_fft::pad_index(B.y0 + yy)] = cplx{v[k].x, v[k].y};
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- passes ----
+  const pa_fft::Radices R = pa_fft::radices_of(p.logL);
+  const cplx* twp = p.tw;
+  auto tw = [twp](int i) {
+    const double2 w = __ldg(reinterpret_cast<const double2*>(twp) + i);
+    return cplx{w.x, w.y};
+  };
+  int M = p.L;
+#pragma unroll 1
+  for (int ps = 0; ps < R.n; ++ps) {
+    const int r = R.r[ps];
+    const int per_line = p.L / r;
+    const int total = ncol * per_line;
+    for (int w = t; w < total; w += FFT_THREADS) {
+      SmLine x{sm + (w / per_line) * p.pitch};
+      const int u = w % per_line;
+      if (r == 8) pa_fft::butterfly<8>(x, u, p.L, M, p.sign, tw);
+      else if (r == 4) pa_fft::butterfly<4>(x, u, p.L, M, p.sign, tw);
+      else pa_fft::butterfly<2>(x, u, p.L, M, p.sign, tw);
+    }
+    M /= r;
+    __syncthreads();
+  }
+
+  // ---- store: natural order, every line one contiguous run ----
+  char* d = p.dst + x0 * p.dsx;
+#pragma unroll 1
+  for (int i = 0; i < p.no; ++i) d += ok[i] * p.dso[i];
+  for (int c = 0; c < ncol; ++c) {
+    const cplx* line = sm + c * p.pitch;
+    double2* out = reinterpret_cast<double2*>(d + c * p.dsx);
+    for (int k = t; k < p.L; k += FFT_THREADS) {
+      const cplx v = line[pa_fft::pad_index(pa_fft::fft_position_of(k, p.L, R))];
+      __stcs(out + k, make_double2(v.x, v.y));
+    }
+  }
+}
+
+// forward twiddle table W_L^k per (device, L), computed once in extended precision
+static const cplx* twiddles(int L) {
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, cplx*> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto key = std::make_pair(dev, L);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  std::vector<cplx> h(L);
+  for (int k = 0; k < L; ++k) {
+    const long double a = -2.0L * 3.141592653589793238462643383279502884L * k / L;
+    h[k] = cplx{(double)cosl(a), (double)sinl(a)};
+  }
+  cplx* d = nullptr;
+  if (cudaMalloc((void**)&d, sizeof(cplx) * L) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), sizeof(cplx) * L, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  cache[key] = d;
+  return d;
+}
+
+// `blocks[i]` moves block i from `srcs[i]` (recv_buf, or the src parent for the fused
+// self block) into `dst`; together they must tile the destination box.
+pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* srcs, void* dst,
+                     int sign, void* stream) {
+  FftParams p;
+  memset(&p, 0, sizeof p);
+  // the line dim: destination stride 1 (and extent > 1) in some block
+  int jy = -1;
+  for (int b = 0; b < nb && jy < 0; ++b)
+    for (int i = 0; i < blocks[b]->nd_raw; ++i)
+      if (blocks[b]->raw[i].e > 1 && blocks[b]->raw[i].ds == 1) {
+        jy = i;
+        break;
+      }
+  if (jy < 0) {
+    set_error("fused FFT: the destination has no contiguous dimension longer than 1");
+    return PA_EINVAL;
+  }
+  if (jy == 0) {
+    set_error("fused FFT: the transform axis is contiguous in the source too (no transposition "
+              "to fuse with); transform it in place instead");
+    return PA_EINVAL;
+  }
+  i64 min_doff = -1;
+  const BlockCopy* ref = nullptr;
+  for (int b = 0; b < nb; ++b) {
+    const BlockCopy& B = *blocks[b];
+    if (B.count == 0) continue;
+    if (B.elsize != 16) {
+      set_error("fused FFT: ComplexF64 (16-byte) elements only");
+      return PA_EINVAL;
+    }
+    if (B.raw[0].ss != 1) {
+      set_error("fused FFT: unexpected source layout");
+      return PA_EINVAL;
+    }
+    if (!ref) ref = &B;
+    if (B.nd_raw != ref->nd_raw) return PA_EINVAL;
+    for (int i = 0; i < B.nd_raw; ++i)
+      if (i != jy && (B.raw[i].e != ref->raw[i].e || B.raw[i].ds != ref->raw[i].ds)) {
+        set_error("fused FFT: the blocks do not share their line set");
+        return PA_EINVAL;
+      }
+    if (min_doff < 0 || B.dst_off < min_doff) min_doff = B.dst_off;
+  }
+  if (!ref) return PA_OK;  // nothing to do on this rank
+  i64 L = 0;
+  for (int b = 0; b < nb; ++b) {
+    const BlockCopy& B = *blocks[b];
+    if (B.count == 0) continue;
+    if (p.nb >= FFT_MAXB) {
+      set_error("fused FFT: more than %d blocks", FFT_MAXB);
+      return PA_EINVAL;
+    }
+    FftBlock& F = p.blk[p.nb++];
+    F.src = (const char*)srcs[b] + B.src_off * 16;
+    F.y0 = (int)(B.dst_off - min_doff);
+    F.ey = (int)B.raw[jy].e;
+    F.ssy = B.raw[jy].ss * 16;
+    int o = 0;
+    for (int i = 1; i < B.nd_raw; ++i)
+      if (i != jy && B.raw[i].e > 1) F.so[o++] = B.raw[i].ss * 16;
+    L += B.raw[jy].e;
+  }
+  int logL = 0;
+  while ((1LL << logL) < L) ++logL;
+  if ((1LL << logL) != L || L < 8 || L > 1024) {
+    set_error("fused FFT: line length %lld is not a power of two in 8..1024", (long long)L);
+    return PA_EINVAL;
+  }
+  // the blocks must tile [0, L) without gaps
+  {
+    std::vector<std::pair<int, int>> seg;
+    for (int b = 0; b < p.nb; ++b) seg.push_back({p.blk[b].y0, p.blk[b].ey});
+    std::sort(seg.begin(), seg.end());
+    int pos = 0;
+    for (auto& s : seg) {
+      if (s.first != pos) {
+        set_error("fused FFT: the blocks do not tile the transform axis");
+        return PA_EINVAL;
+      }
+      pos += s.second;
+    }
+  }
+  p.dst = (char*)dst + min_doff * 16;
+  p.ex = ref->raw[0].e;
+  p.dsx = ref->raw[0].ds * 16;
+  p.no = 0;
+  for (int i = 1; i < ref->nd_raw; ++i)
+    if (i != jy && ref->raw[i].e > 1) {
+      if (p.no >= FFT_MAXO) return PA_EINVAL;
+      p.oe[p.no] = ref->raw[i].e;
+      p.dso[p.no] = ref->raw[i].ds * 16;
+      ++p.no;
+    }
+  p.L = (int)L;
+  p.logL = logL;
+  p.sign = sign < 0 ? -1 : 1;
+  p.pitch = pa_fft::padded_pitch((int)L);
+  p.tw = twiddles((int)L);
+  if (!p.tw) {
+    set_error("fused FFT: twiddle table allocation failed");
+    cudaGetLastError();
+    return PA_ENOMEM;
+  }
+  p.tiles_x = (unsigned)((p.ex + FFT_C - 1) / FFT_C);
+  unsigned long long grid = p.tiles_x;
+  for (int i = 0; i < p.no; ++i) grid *= (unsigned long long)p.oe[i];
+  if (grid == 0) return PA_OK;
+  if (grid > 0x7fffffffULL) {
+    set_error("fused FFT: too many lines for one launch");
+    return PA_EINVAL;
+  }
+  const size_t smem = sizeof(cplx) * (size_t)FFT_C * p.pitch;
+  static int attr_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_dev[dev]) {
+    cudaFuncSetAttribute(k_unpack_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (dev >= 0 && dev < 64) attr_dev[dev] = 1;
+  }
+  cudaGetLastError();
+  k_unpack_fft<<<(unsigned)grid, FFT_THREADS, smem, (cudaStream_t)stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("fused FFT kernel launch failed: %s", cudaGetErrorString(e));
+    return PA_ECUDA;
+  }
+  count_launch();
+  return PA_OK;
+}
+
+}  // namespace pa

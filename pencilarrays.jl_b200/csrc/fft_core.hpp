@@ -1,0 +1,142 @@
+// Radix passes of the in-shared-memory 1-d complex FFT that the fused
+// unpack+FFT kernel (fft.cu) runs on every line it has just transposed.
+// the permutation of a pencil exists to make the FFT axis
+// contiguous (/root/reference/docs/src/Pencils.md:210-214,
+// docs/src/Transpositions.md:7-9) -- here the transform is applied before the
+// line ever leaves the SM.
+//
+// Algorithm: decimation in frequency (Gentleman-Sande), mixed radix
+// {2, 4, 8}, in place.  A pass of radix R over sub-length M takes, for every
+// group g and offset j < M/R, the R points x[g*M + j + q*M/R], replaces them
+// by their R-point DFT and multiplies output s by W_M^(j*s).  After all
+// passes the element at position p = s1*L/R1 + s2*L/(R1*R2) + ... holds
+// X[s1 + R1*(s2 + R2*(...))]: fft_position_of() inverts that for the final
+// natural-order read-out.  Twiddles come from a table W_L^k = exp(-2*pi*i*k/L),
+// k < L, computed on the host in extended precision; the backward transform
+// conjugates them (unnormalised, like FFTW / PencilFFTs).
+//
+// Everything is __host__ __device__ so that tests/fft_host_check.cpp can run
+// the very same index arithmetic and butterflies on the CPU against numpy.fft.
+#pragma once
+
+#if defined(__CUDACC__)
+#define PA_HD __host__ __device__ __forceinline__
+#else
+#define PA_HD inline
+#endif
+
+namespace pa_fft {
+
+struct cplx {
+  double x, y;
+};
+
+PA_HD cplx cadd(cplx a, cplx b) { return cplx{a.x + b.x, a.y + b.y}; }
+PA_HD cplx csub(cplx a, cplx b) { return cplx{a.x - b.x, a.y - b.y}; }
+PA_HD cplx cmul(cplx a, cplx b) { return cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// multiplication by -i (forward) / +i (backward): sign = -1 forward, +1 backward
+PA_HD cplx mul_i(cplx a, int sign) { return sign < 0 ? cplx{a.y, -a.x} : cplx{-a.y, a.x}; }
+
+// storage index of logical position i: one pad element after every 8, 64 and 512
+// elements, so that accesses at every power-of-8 stride (the strides of the radix-8
+// passes and of the digit-reversed read-out) fall into different 16-byte bank groups
+PA_HD int pad_index(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+// elements per padded line, forced to 1 mod 8 (the C lines of a CTA are written
+// column-wise by 8 consecutive threads)
+PA_HD int padded_pitch(int L) {
+  int n = pad_index(L - 1) + 1;
+  while ((n & 7) != 1) ++n;
+  return n;
+}
+
+constexpr int MAX_PASSES = 5;
+struct Radices {
+  int n;
+  int r[MAX_PASSES];
+};
+
+// small radix first (its stride is the longest: conflict-free), then radix 8
+PA_HD Radices radices_of(int logL) {
+  Radices R;
+  R.n = 0;
+  int rem = logL % 3;
+  if (rem == 1) R.r[R.n++] = 2;
+  if (rem == 2) R.r[R.n++] = 4;
+  for (int i = 0; i < logL / 3; ++i) R.r[R.n++] = 8;
+  return R;
+}
+
+// position (after all passes) of output frequency k
+PA_HD int fft_position_of(int k, int L, const Radices& R) {
+  int p = 0, stride = L;
+  for (int i = 0; i < R.n; ++i) {
+    stride /= R.r[i];
+    p += (k % R.r[i]) * stride;
+    k /= R.r[i];
+  }
+  return p;
+}
+
+// R-point DFT in registers, a[q] -> A[s] = sum_q a[q] * w^(q*s), w = exp(sign*2*pi*i/R)
+PA_HD void dft2(cplx* a) {
+  cplx t = a[0];
+  a[0] = cadd(t, a[1]);
+  a[1] = csub(t, a[1]);
+}
+PA_HD void dft4(cplx* a, int sign) {
+  cplx t0 = cadd(a[0], a[2]), t1 = csub(a[0], a[2]);
+  cplx t2 = cadd(a[1], a[3]), t3 = mul_i(csub(a[1], a[3]), sign);
+  a[0] = cadd(t0, t2);
+  a[1] = cadd(t1, t3);
+  a[2] = csub(t0, t2);
+  a[3] = csub(t1, t3);
+}
+PA_HD void dft8(cplx* a, int sign) {
+  const double h = 0.70710678118654752440;
+  // even / odd 4-point transforms
+  cplx e[4] = {a[0], a[2], a[4], a[6]};
+  cplx o[4] = {a[1], a[3], a[5], a[7]};
+  dft4(e, sign);
+  dft4(o, sign);
+  // o[s] *= w8^s, w8 = exp(sign*i*pi/4)
+  cplx w1 = cplx{h, sign * h}, w3 = cplx{-h, sign * h};
+  o[1] = cmul(o[1], w1);
+  o[2] = mul_i(o[2], sign);
+  o[3] = cmul(o[3], w3);
+  for (int s = 0; s < 4; ++s) {
+    a[s] = cadd(e[s], o[s]);
+    a[s + 4] = csub(e[s], o[s]);
+  }
+}
+
+// One butterfly `u` (< L/R) of a pass with radix R over sub-length M on one line.
+// `at(i)` maps a logical position to the (padded) storage; tw = forward table W_L^k.
+template <int R, class Line, class Tw>
+PA_HD void butterfly(Line& x, int u, int L, int M, int sign, const Tw& tw) {
+  const int Q = M / R;            // stride between the R inputs
+  const int g = u / Q, j = u % Q;
+  const int base = g * M + j;
+  cplx a[R];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q = 0; q < R; ++q) a[q] = x.get(base + q * Q);
+  if (R == 2) dft2(a);
+  if (R == 4) dft4(a, sign);
+  if (R == 8) dft8(a, sign);
+  const int step = j * (L / M);   // W_M^(j*s) = W_L^(j*s*L/M)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int s = 0; s < R; ++s) {
+    cplx v = a[s];
+    if (s > 0 && step > 0) {
+      cplx w = tw((step * s) & (L - 1));
+      if (sign > 0) w.y = -w.y;
+      v = cmul(v, w);
+    }
+    x.put(base + s * Q, v);
+  }
+}
+
+}  // namespace pa_fft

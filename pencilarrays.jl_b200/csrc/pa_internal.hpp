@@ -257,6 +257,11 @@ pa_status host_chain_buffer(HostChain* c, int slot, int which, void** p, i64* by
 pa_status host_chain_time_begin(HostChain* c);
 pa_status host_chain_time_end(HostChain* c, float* ms);
 
+// fused unpack + 1-d FFT along the destination's contiguous dim (fft.cu): the blocks
+// together tile the destination box; srcs[i] = base pointer blocks[i] reads from
+pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* srcs, void* dst,
+                     int sign, void* stream);
+
 // standalone flag step on `stream`: signal the n remote words (monotonic max,
 // release at system scope) and/or wait for the n local words to reach seq
 pa_status launch_flags(int n, unsigned long long* const* remote, unsigned long long* const* local,

@@ -838,9 +838,12 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   // same stream (fused K3: src -> dest in one pass) and fills the HBM time the
   // NVLink-bound exchange leaves idle.  tunable "self_first" = 1 restores the
   // reference's order (self block packed first, :393-403).
+  const int fft_sign = (flags & PA_FFT_FORWARD) ? -1 : ((flags & PA_FFT_BACKWARD) ? 1 : 0);
   const bool self_first = stage_self || g_tun.self_first;
   if (stage_self) {
     RC(launch_block(self.pack, src, rbuf, S.pack_s, nullptr));  // tail of recv_buf (:393-403)
+  } else if (fft_sign) {
+    // (the fused unpack+FFT kernel gathers the self block straight out of src)
   } else if (self_first) {
     RC(launch_block(P->self_fused, src, dst, S.unpack_s, nullptr));  // K3, one pass
   }
@@ -853,7 +856,7 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   }
   CU(cudaEventRecord(S.ev_allpacked, S.pack_s));
   if (timing) CU(cudaEventRecord(S.t[1], S.pack_s));
-  if (!self_first) RC(launch_block(P->self_fused, src, dst, S.pack_s, nullptr, cap));
+  if (!self_first && !fft_sign) RC(launch_block(P->self_fused, src, dst, S.pack_s, nullptr, cap));
   CU(cudaEventRecord(S.ev_self_done, S.pack_s));
 
   // ---- 2. exchange -------------------------------------------------------------
@@ -947,7 +950,7 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
         }
       }
     }
-    if (ipc && !overlap) {
+    if (ipc && (!overlap || fft_sign)) {
       // sequential phases: every block has landed before the first unpack
       for (int k = 1; k < nproc; ++k)
         for (int c = 0; c < C; ++c) {
@@ -1008,8 +1011,24 @@ static pa_status staged(Plan* P, Comm* comm, const void* src, void* dst, unsigne
   // the reference finishes transpose_send! before transpose_recv! (:326-340).
   if (stage_self) CU(cudaStreamWaitEvent(S.unpack_s, S.ev_allpacked, 0));
   if (timing) CU(cudaEventRecord(S.t[4], S.unpack_s));
-  if (stage_self) RC(launch_block(self.unpack, rbuf, dst, S.unpack_s, nullptr));  // local data first (:511)
-  if (p2p && overlap) {
+  if (fft_sign) {
+    // ONE kernel: gather every block (remote ones from recv_buf, the self block from src
+    // or from the tail of recv_buf), transform along the now-local contiguous dim, store
+    CU(cudaStreamWaitEvent(S.unpack_s, S.ev_comm_done, 0));
+    std::vector<const BlockCopy*> bl;
+    std::vector<const void*> sp;
+    for (int n = 0; n < nproc; ++n) {
+      const bool fused_self = (n == me) && !stage_self;
+      bl.push_back(fused_self ? &P->self_fused : &P->peers[n].unpack);
+      sp.push_back(fused_self ? src : (const void*)rbuf);
+    }
+    RC(unpack_fft(nproc, bl.data(), sp.data(), dst, fft_sign, S.unpack_s));
+  } else if (stage_self) {
+    RC(launch_block(self.unpack, rbuf, dst, S.unpack_s, nullptr));  // local data first (:511)
+  }
+  if (fft_sign) {
+    // (nothing else to unpack)
+  } else if (p2p && overlap) {
     for (int k = 1; k < nproc; ++k) {
       const int from = from_of[k];
       for (int c = 0; c < C; ++c) {
@@ -1066,6 +1085,24 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   }
   if (timing) CU(cudaEventRecord(S.t[0], user));
 
+  const int fft_sign = (flags & PA_FFT_FORWARD) ? -1 : ((flags & PA_FFT_BACKWARD) ? 1 : 0);
+  if (fft_sign && src && dst &&
+      (src == dst || ranges_overlap(src, P->length_in * ES, dst, P->length_out * ES))) {
+    set_error("fused FFT: src and dst must not alias");
+    return PA_EINVAL;
+  }
+  if (fft_sign && (P->dim < 0 || P->nproc == 1)) {
+    // one block: the whole local array, src -> fft(permuted dest)
+    if (P->length_out == 0) return PA_OK;
+    const BlockCopy* b = &P->self_fused;
+    RC(unpack_fft(1, &b, &src, dst, fft_sign, user));
+    if (timing) {
+      CU(cudaEventRecord(S.t[6], user));
+      S.timed_once = true;
+    }
+    return PA_OK;
+  }
+
   if (P->dim < 0) {
     void* scratch = nullptr;
     const i64 bytes = P->length_out * ES;
@@ -1095,6 +1132,11 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
       src && dst && (src == dst || ranges_overlap(src, P->length_in * ES, dst, P->length_out * ES));
   const bool stage_self = aliased || (flags & PA_STAGE_SELF);
   const bool one = (P->method == PA_PEER_PUT || P->method == PA_PEER_GET) && !stage_self && nproc > 1;
+  if (fft_sign && one) {
+    set_error("fused FFT: the one-sided methods have no unpack pass to fuse with; use "
+              "PointToPoint / Alltoallv");
+    return PA_EINVAL;
+  }
   if (!one) {
     // (one-sided puts/gets need no staging arenas)
     i64 need_send = nproc > 1 ? std::max<i64>(1, P->send_elems * ES) : 0;

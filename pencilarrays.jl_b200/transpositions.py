@@ -286,8 +286,12 @@ def Waitall(t: Transposition):
     return None
 
 
-def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False):
-    """``transpose!(dest, src; method)`` or ``transpose!(t; waitall)`` (:160-179)."""
+def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False, fft=None):
+    """``transpose!(dest, src; method)`` or ``transpose!(t; waitall)`` (:160-179).
+
+    ``fft="forward"`` / ``"backward"`` (B200 extension): the unpack and the
+    1-d complex FFT along ``dest``'s contiguous dimension -- the step a PencilFFTs-style
+    plan runs next -- execute as one kernel; ``dest`` receives the transformed array."""
     if len(args) == 1 and isinstance(args[0], Transposition):
         t = args[0]
     elif len(args) == 2:
@@ -300,6 +304,13 @@ def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False)
         raise TypeError("transpose_(dest, src; method) or transpose_(t; waitall)")
     flags = (_lib.PA_WAITALL if waitall else 0) | (0 if overlap else _lib.PA_NO_OVERLAP) | (
         _lib.PA_STAGE_SELF if stage_self else 0)
+    if fft is not None:
+        if fft in ("forward", -1):
+            flags |= _lib.PA_FFT_FORWARD
+        elif fft in ("backward", 1):
+            flags |= _lib.PA_FFT_BACKWARD
+        else:
+            raise ArgumentError(_lib.PA_EINVAL, "fft must be 'forward' or 'backward'")
     comm = t.Pi.topology.comm.handle
     # (an empty local array may have a null data pointer: the library accepts that)
     check(lib.pa_transpose(t.plan.h, comm, C.c_void_p(t.Ai.data_ptr() or None),

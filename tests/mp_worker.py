@@ -117,6 +117,7 @@ def main():
                 np.ascontiguousarray(cur_o[rank].data.reshape(-1, order="F")).view(np.uint8).copy()))
             torch.cuda.synchronize()
         for k in range(1, len(case["chain"])):
+            cur_in = cur
             nxt_o = [O.OArray.undef(dtype, po, *extra) for po in opens[k]]
             O.transpose_all(nxt_o, cur_o)
             want = np.ascontiguousarray(nxt_o[rank].data.reshape(-1, order="F"))
@@ -142,6 +143,41 @@ def main():
                         (case["name"], k, rank, method, overlap, waitall, tun)
                 for name, v in defaults.items():
                     pa.set_tunable(name, v)
+                if case["name"].startswith("c128_"):
+                    # fused unpack + FFT along the now-local contiguous dim (staged methods) on a
+                    # NUMERIC field (the bit-pattern field holds NaNs and 1e300s): numpy.fft of
+                    # the same global array cut for the destination pencil, FFT's own tolerance
+                    rng = np.random.default_rng(5)
+                    shape = tuple(case["dims"]) + tuple(extra)
+                    G = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+                    Gb = np.ascontiguousarray(G.reshape(-1, order="F")).view(np.uint8) \
+                        .reshape(-1, 16).reshape(shape + (16,), order="F")
+                    a_in = O.scatter(Gb, opens[k - 1], extra, dtype)[rank]
+                    a_out = O.scatter(Gb, opens[k], extra, dtype)[rank]
+                    src = pa.PencilArray.undef(tdt, pens[k - 1], *extra)
+                    src.data.view(torch.uint8).reshape(-1).copy_(torch.from_numpy(
+                        np.ascontiguousarray(a_in.data.reshape(-1, order="F")).view(np.uint8).copy()))
+                    L = a_out.data.shape[0]
+                    ok_shape = case["name"].startswith("c128_pow2")  # power-of-two lines, 8..1024
+                    for method in (pa.PointToPoint(), pa.Alltoallv()):
+                        for direction in ("forward", "backward"):
+                            out = pa.PencilArray.undef(tdt, pens[k], *extra)
+                            t = pa.Transposition(out, src, method=method)
+                            if not ok_shape:
+                                try:
+                                    pa.transpose_(t, fft=direction)
+                                    raise AssertionError("fused FFT accepted an unsupported shape")
+                                except pa.ArgumentError:
+                                    continue
+                            pa.transpose_(t, fft=direction)
+                            torch.cuda.synchronize()
+                            ref = np.fft.fft(a_out.data, axis=0) if direction == "forward" else \
+                                np.fft.ifft(a_out.data, axis=0) * L
+                            got = np.ascontiguousarray(out.data.cpu().numpy()).reshape(-1)
+                            want_f = np.ascontiguousarray(ref.reshape(-1, order="F"))
+                            tol = 8 * np.finfo(np.float64).eps * np.log2(L) * np.abs(want_f).max()
+                            assert np.abs(got - want_f).max() <= tol, \
+                                ("fft", case["name"], k, rank, method, direction)
                 cur = nxt
             cur_o = nxt_o
         if mode != "gloo" and len(case["chain"]) >= 3 and not extra:

@@ -230,3 +230,59 @@ def test_empty_local_array_null_pointers():
     plan = _Plan(qx, qy, (), 4, pa.PointToPoint())
     st = lib.pa_transpose(plan.h, None, None, None, 1, stream_ptr())
     assert st == pa._lib.PA_EINVAL
+
+
+# ---------------------------------------------------------------------------- fused unpack + FFT
+def test_fft_core_on_cpu_matches_numpy(tmp_path):
+    """(runs the shared butterfly / indexing core on the host -- see also the CPU suite)"""
+    import test_fft_core
+    test_fft_core.test_fft_core_matches_numpy(tmp_path)
+
+
+@pytest.mark.parametrize("dims,perms", [((8, 64, 4), ((2, 1, 3), (3, 2, 1))),
+                                        ((24, 8, 16), ((2, 1, 3), (3, 2, 1))),
+                                        ((12, 256, 8), ((2, 3, 1), (3, 1, 2))),
+                                        ((9, 512, 3), ((2, 1, 3), (3, 2, 1))),
+                                        ((16, 1024, 8), ((2, 3, 1), (3, 1, 2)))])
+@pytest.mark.parametrize("direction", ["forward", "backward"])
+def test_fused_unpack_fft_single_rank(dims, perms, direction):
+    """transpose!(…; fft=…) == numpy.fft along the new contiguous dim of the plain
+    transpose! result, at the FFT's own tolerance (8 eps log2(L) max|X|)."""
+    _, (ux, uy, uz) = _single_rank_chain(dims, torch.complex128, perms)
+    ux.data.view(torch.float64).normal_()
+    for dst, src in ((uy, ux), (uz, uy)):
+        t = pa.Transposition(dst, src)
+        pa.transpose_(t)
+        torch.cuda.synchronize()
+        plain = dst.data.cpu().numpy()           # torch (row-major) shape: contiguous dim LAST
+        L = plain.shape[-1]
+        fused = pa.PencilArray.undef(torch.complex128, dst.pencil)
+        t2 = pa.Transposition(fused, src)
+        if L < 8 or L & (L - 1):
+            with pytest.raises(pa.ArgumentError):
+                pa.transpose_(t2, fft=direction)
+            continue
+        n0 = pa.launch_count()
+        pa.transpose_(t2, fft=direction)
+        torch.cuda.synchronize()
+        assert pa.launch_count() - n0 == 1       # ONE kernel: unpack and transform
+        ref = np.fft.fft(plain, axis=-1) if direction == "forward" else np.fft.ifft(plain, axis=-1) * L
+        tol = 8 * np.finfo(np.float64).eps * np.log2(L) * np.abs(ref).max()
+        assert np.abs(fused.data.cpu().numpy() - ref).max() <= tol
+
+
+def test_fused_fft_refusals():
+    _, (ux, uy, uz) = _single_rank_chain((16, 32, 8), torch.complex128, ((2, 1, 3), (3, 2, 1)))
+    with pytest.raises(pa.ArgumentError):      # aliased src / dst
+        check(lib.pa_transpose(pa.Transposition(uy, ux).plan.h, None, ptr(ux.data), ptr(ux.data),
+                               1 | pa._lib.PA_FFT_FORWARD, stream_ptr()))
+    _, (fx, fy, fz) = _single_rank_chain((16, 32, 8), torch.float64, ((2, 1, 3), (3, 2, 1)))
+    with pytest.raises(pa.ArgumentError):      # not ComplexF64
+        pa.transpose_(pa.Transposition(fy, fx), fft="forward")
+    # same contiguous dim on both sides: nothing is transposed, nothing to fuse with
+    topo = pa.MPITopology(pa.COMM_SELF, (1, 1))
+    px = pa.Pencil(topo, (16, 32, 8), (2, 3))
+    p2 = pa.Pencil(px, decomp_dims=(1, 3), permute=pa.Permutation(1, 3, 2))
+    a, b = pa.PencilArray.undef(torch.complex128, px), pa.PencilArray.undef(torch.complex128, p2)
+    with pytest.raises(pa.ArgumentError):
+        pa.transpose_(pa.Transposition(b, a), fft="forward")

@@ -163,6 +163,11 @@ CASES = [
     dict(name="cfg4_small_4x2", grid=(4, 2), dims=(16, 32, 16), extra=(), it=16,
          chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1)), ((1, 3), (2, 1, 3)),
                 ((2, 3), None)]),
+    # ComplexF64, power-of-two local lines: the shapes the fused unpack+FFT kernel accepts
+    dict(name="c128_pow2_2x2", grid=(2, 2), dims=(16, 32, 64), extra=(), it=16,
+         chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1))]),
+    dict(name="c128_pow2_2x1", grid=(2, 1), dims=(32, 16, 8), extra=(3,), it=16,
+         chain=[((2, 3), None), ((1, 3), (2, 1, 3)), ((1, 2), (3, 2, 1))]),
     # 2-byte elements, extra dim, 4-D data
     dict(name="u16_4d", grid=(2, 2), dims=(6, 5, 4, 7), extra=(2,), it=2,
          chain=[((3, 4), None), ((1, 4), (4, 3, 2, 1)), ((1, 2), (3, 4, 1, 2))]),
