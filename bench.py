@@ -398,6 +398,31 @@ def baseline_kernels(pa, torch, peak):
     return out
 
 
+def fused_fft_rows(pa, torch, peak):
+    """transpose! with the 1-d FFT of the next step fused into its unpack
+    (PA_FFT_FORWARD), against the unfused pair (this library's transpose! + cuFFT through
+    torch.fft -- library code, the baseline).  512^3 ComplexF64, one GPU."""
+    topo1 = pa.MPITopology(pa.COMM_SELF, (1, 1))
+    dims = (512, 512, 512)
+    px = pa.Pencil(topo1, dims, (2, 3))
+    py = pa.Pencil(px, decomp_dims=(1, 3), permute=pa.Permutation(2, 1, 3))
+    ux, uy = pa.PencilArray.undef(torch.complex128, px), pa.PencilArray.undef(torch.complex128, py)
+    ux.data.view(torch.float64).normal_()
+    t = pa.Transposition(uy, ux)
+    tmp = torch.empty_like(uy.data)
+    nb = 2 * ux.data.numel() * 16
+    ms_tf = time_launches(lambda: (pa.transpose_(t), torch.fft.fft(uy.data, dim=-1, out=tmp)), 5, torch)
+    pa.transpose_(t)
+    torch.fft.fft(uy.data, dim=-1, out=tmp)
+    ms_fused = time_launches(lambda: pa.transpose_(t, fft="forward"), 5, torch)
+    err = float((uy.data - tmp).abs().max() / tmp.abs().max())
+    return {"shape": "512^3 ComplexF64, x->y (2,1,3), 512-point lines",
+            "fused_ms": round(ms_fused, 4), "unfused_ms": round(ms_tf, 4),
+            "speedup": round(ms_tf / ms_fused, 3), "fused_alg_bytes": nb,
+            "fused_GBps": round(nb / ms_fused / 1e6, 1), "fused_frac_of_hbm": round(nb / ms_fused / 1e6 / peak, 4),
+            "max_rel_diff_vs_cufft": err}
+
+
 def configs1_256cubed(pa, torch, peak):
     """BASELINE configs[1]: 256^3 Float64, 1 GPU, x->y for every permutation = one
     fused K3 launch per transpose!.  Two timings: `rotating` -- 24 back-to-back
@@ -764,6 +789,10 @@ def run_b200(args):
 
     # ---- BASELINE configs[1] beside it (N == 1): 256^3 Float64, 1 GPU, pack/unpack kernel only ----
     cfg1 = configs1_256cubed(pa, torch, peak) if (n == 1 and args.workload == "cfg4" and not args.quick) else None
+    fused = None
+    if n == 1 and args.workload == "cfg4" and not args.quick:
+        torch.cuda.empty_cache()
+        fused = fused_fft_rows(pa, torch, peak)
     if cfg1:
         for k, v in cfg1.items():
             if isinstance(v, dict):
@@ -886,6 +915,7 @@ def run_b200(args):
                 "timing": "CUDA events on the launching stream, back-to-back launches, this run"},
             "kernels": kern,
             "configs1_256cubed_f64": cfg1,
+            "fused_fft": fused,
             "methods": others,
             "sections": sections,
             "cpu_baseline": cpu,

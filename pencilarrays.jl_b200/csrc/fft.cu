@@ -8,7 +8,7 @@
 // the FFT reads and rewrites it.  This kernel does both in one:
 //
 //   * a CTA owns C = 8 consecutive destination LINES (same outer coordinates,
-//     8 consecutive values of the source-contiguous dim);
+//     8 consecutive values of the source-contiguous dim; 4 for 1024-point lines);
 //   * it gathers them from EVERY block of the transposition -- the blocks the
 //     peers sent (dense in recv_buf, wire layout of :380-416) and the self block
 //     straight out of `src` -- with 128-byte (8 x ComplexF64) coalesced loads,
@@ -35,10 +35,12 @@ namespace pa {
 
 using pa_fft::cplx;
 
-constexpr int FFT_C = 8;      // lines per CTA
 constexpr int FFT_MAXB = 8;   // blocks gathered by one launch (ranks of a grid line on one box)
 constexpr int FFT_MAXO = PA_MAX_DIMS - 2;
 constexpr int FFT_THREADS = 256;
+// lines per CTA: 8 (128-byte gathers); 4 for 1024-point lines so that three CTAs still
+// share an SM's shared memory (75 KB each)
+constexpr int fft_lines(int logL) { return logL >= 10 ? 4 : 8; }
 
 struct FftBlock {
   const char* src;  // block origin
@@ -65,84 +67,121 @@ struct SmLine {
   __device__ __forceinline__ void put(int i, cplx v) { p[pa_fft::pad_index(i)] = v; }
 };
 
+// radix of the pass that starts at sub-length 2^LOGM (the odd bits go first: radices_of)
+template <int LOGM>
+struct PassRadix {
+  static constexpr int LOGR = (LOGM % 3 == 0) ? 3 : (LOGM % 3);
+};
+
+template <int LOGL, int LOGM, int C, class Tw>
+__device__ __forceinline__ void fft_passes(cplx* sm, int pitch, int ncol, int sign, const Tw& tw) {
+  if constexpr (LOGM > 0) {
+    constexpr int LOGR = PassRadix<LOGM>::LOGR;
+    constexpr int R = 1 << LOGR, L = 1 << LOGL, M = 1 << LOGM;
+    constexpr int PER_LINE = L / R;
+    constexpr int TOTAL = C * PER_LINE;
+#pragma unroll
+    for (int w0 = 0; w0 < TOTAL; w0 += FFT_THREADS) {
+      const int w = w0 + (int)threadIdx.x;
+      const int c = w / PER_LINE, u = w % PER_LINE;
+      if (w < TOTAL && c < ncol) {
+        SmLine x{sm + c * pitch};
+        pa_fft::butterfly<R>(x, u, L, M, sign, tw);
+      }
+    }
+    __syncthreads();
+    fft_passes<LOGL, LOGM - LOGR, C>(sm, pitch, ncol, sign, tw);
+  }
+}
+
+// storage position of output frequency k (fft_position_of with compile-time radices)
+template <int LOGL, int LOGM>
+__device__ __forceinline__ int fft_pos(int k) {
+  if constexpr (LOGM == 0) {
+    return 0;
+  } else {
+    constexpr int LOGR = PassRadix<LOGM>::LOGR;
+    return ((k & ((1 << LOGR) - 1)) << (LOGM - LOGR)) + fft_pos<LOGL, LOGM - LOGR>(k >> LOGR);
+  }
+}
+
+template <int LOGL, int C>
 __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constant__ FftParams p) {
+  constexpr int L = 1 << LOGL;
   extern __shared__ __align__(16) unsigned char fft_smem[];
   cplx* sm = reinterpret_cast<cplx*>(fft_smem);
   const int t = threadIdx.x;
   unsigned long long bid = blockIdx.x;
-  const long long x0 = (long long)(bid % p.tiles_x) * FFT_C;
+  const long long x0 = (long long)(bid % p.tiles_x) * C;
   bid /= p.tiles_x;
-  long long ok[FFT_MAXO];
+  long long so_off[FFT_MAXB];
+#pragma unroll
+  for (int b = 0; b < FFT_MAXB; ++b) so_off[b] = 0;
+  long long d_off = 0;
 #pragma unroll 1
   for (int i = 0; i < p.no; ++i) {
-    ok[i] = (long long)(bid % (unsigned long long)p.oe[i]);
+    const long long k = (long long)(bid % (unsigned long long)p.oe[i]);
     bid /= (unsigned long long)p.oe[i];
+    d_off += k * p.dso[i];
+#pragma unroll
+    for (int b = 0; b < FFT_MAXB; ++b)
+      if (b < p.nb) so_off[b] += k * p.blk[b].so[i];
   }
-  const int ncol = (int)((p.ex - x0) < FFT_C ? (p.ex - x0) : FFT_C);
+  const int ncol = (int)((p.ex - x0) < C ? (p.ex - x0) : C);
+  const int pitch = p.pitch;
 
-  // ---- gather: 8 threads read 8 consecutive columns (128 B) of one source row ----
+  // ---- gather: C threads read C consecutive columns (C x 16 B) of one source row;
+  //      8 rows in flight per thread ----
   {
-    const int c = t % FFT_C, r = t / FFT_C;  // 32 rows per sweep
-    constexpr int RS = FFT_THREADS / FFT_C;
-    cplx* line = sm + c * p.pitch;
-#pragma unroll 1
-    for (int b = 0; b < p.nb; ++b) {
-      const FftBlock& B = p.blk[b];
-      const char* s = B.src + (x0 + c) * (long long)sizeof(cplx);
-#pragma unroll 1
-      for (int i = 0; i < p.no; ++i) s += ok[i] * B.so[i];
-      for (int y = r; y < B.ey; y += 4 * RS) {
-        double2 v[4];
+    const int c = t % C, r = t / C;
+    constexpr int RS = FFT_THREADS / C;  // rows per sweep
+    constexpr int U = 8;
+    cplx* line = sm + c * pitch;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int yy = y + k * RS;
-          if (c < ncol && yy < B.ey)
-            v[k] = __ldcs(reinterpret_cast<const double2*>(s + (long long)yy * B.ssy));
-        }
+    for (int b = 0; b < FFT_MAXB; ++b) {
+      if (b < p.nb) {
+        const FftBlock& B = p.blk[b];
+        const char* s = B.src + so_off[b] + (x0 + c) * (long long)sizeof(cplx);
+        const int ey = B.ey, y0 = B.y0;
+        const long long ssy = B.ssy;
+        for (int y = r; y < ey; y += U * RS) {
+          double2 v[U];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int yy = y + k * RS;
-          if (c < ncol && yy < B.ey) line[pa_fft::pad_index(B.y0 + yy)] = cplx{v[k].x, v[k].y};
+          for (int k = 0; k < U; ++k) {
+            const int yy = y + k * RS;
+            if (c < ncol && yy < ey) v[k] = __ldcs(reinterpret_cast<const double2*>(s + (long long)yy * ssy));
+          }
+#pragma unroll
+          for (int k = 0; k < U; ++k) {
+            const int yy = y + k * RS;
+            if (c < ncol && yy < ey) line[pa_fft::pad_index(y0 + yy)] = cplx{v[k].x, v[k].y};
+          }
         }
       }
     }
   }
   __syncthreads();
 
-  // ---- passes ----
-  const pa_fft::Radices R = pa_fft::radices_of(p.logL);
+  // ---- passes (radices and strides are compile-time constants) ----
   const cplx* twp = p.tw;
   auto tw = [twp](int i) {
     const double2 w = __ldg(reinterpret_cast<const double2*>(twp) + i);
     return cplx{w.x, w.y};
   };
-  int M = p.L;
-#pragma unroll 1
-  for (int ps = 0; ps < R.n; ++ps) {
-    const int r = R.r[ps];
-    const int per_line = p.L / r;
-    const int total = ncol * per_line;
-    for (int w = t; w < total; w += FFT_THREADS) {
-      SmLine x{sm + (w / per_line) * p.pitch};
-      const int u = w % per_line;
-      if (r == 8) pa_fft::butterfly<8>(x, u, p.L, M, p.sign, tw);
-      else if (r == 4) pa_fft::butterfly<4>(x, u, p.L, M, p.sign, tw);
-      else pa_fft::butterfly<2>(x, u, p.L, M, p.sign, tw);
-    }
-    M /= r;
-    __syncthreads();
-  }
+  fft_passes<LOGL, LOGL, C>(sm, pitch, ncol, p.sign, tw);
 
   // ---- store: natural order, every line one contiguous run ----
-  char* d = p.dst + x0 * p.dsx;
-#pragma unroll 1
-  for (int i = 0; i < p.no; ++i) d += ok[i] * p.dso[i];
+  char* d = p.dst + x0 * p.dsx + d_off;
   for (int c = 0; c < ncol; ++c) {
-    const cplx* line = sm + c * p.pitch;
+    const cplx* line = sm + c * pitch;
     double2* out = reinterpret_cast<double2*>(d + c * p.dsx);
-    for (int k = t; k < p.L; k += FFT_THREADS) {
-      const cplx v = line[pa_fft::pad_index(pa_fft::fft_position_of(k, p.L, R))];
-      __stcs(out + k, make_double2(v.x, v.y));
+#pragma unroll
+    for (int k0 = 0; k0 < L; k0 += FFT_THREADS) {
+      const int k = k0 + t;
+      if (k < L) {
+        const cplx v = line[pa_fft::pad_index(fft_pos<LOGL, LOGL>(k))];
+        __stcs(out + k, make_double2(v.x, v.y));
+      }
     }
   }
 }
@@ -274,7 +313,8 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     cudaGetLastError();
     return PA_ENOMEM;
   }
-  p.tiles_x = (unsigned)((p.ex + FFT_C - 1) / FFT_C);
+  const int C = fft_lines(logL);
+  p.tiles_x = (unsigned)((p.ex + C - 1) / C);
   unsigned long long grid = p.tiles_x;
   for (int i = 0; i < p.no; ++i) grid *= (unsigned long long)p.oe[i];
   if (grid == 0) return PA_OK;
@@ -282,17 +322,30 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     set_error("fused FFT: too many lines for one launch");
     return PA_EINVAL;
   }
-  const size_t smem = sizeof(cplx) * (size_t)FFT_C * p.pitch;
-  static int attr_dev[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_dev[dev]) {
-    cudaFuncSetAttribute(k_unpack_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (dev >= 0 && dev < 64) attr_dev[dev] = 1;
+  const size_t smem = sizeof(cplx) * (size_t)C * p.pitch;
+  cudaError_t e = cudaSuccess;
+  auto launch = [&](auto kern) {
+    // shared memory is the scarce resource: ask for the largest carve-out so that
+    // several CTAs (gather of one, butterflies of another) overlap on an SM
+    static bool configured = false;  // one static per instantiation of this lambda's closure type
+    (void)configured;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
+    kern<<<(unsigned)grid, FFT_THREADS, smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+  };
+  switch (logL) {
+    case 3: launch(k_unpack_fft<3, 8>); break;
+    case 4: launch(k_unpack_fft<4, 8>); break;
+    case 5: launch(k_unpack_fft<5, 8>); break;
+    case 6: launch(k_unpack_fft<6, 8>); break;
+    case 7: launch(k_unpack_fft<7, 8>); break;
+    case 8: launch(k_unpack_fft<8, 8>); break;
+    case 9: launch(k_unpack_fft<9, 8>); break;
+    default: launch(k_unpack_fft<10, 4>); break;
   }
-  cudaGetLastError();
-  k_unpack_fft<<<(unsigned)grid, FFT_THREADS, smem, (cudaStream_t)stream>>>(p);
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("fused FFT kernel launch failed: %s", cudaGetErrorString(e));
     return PA_ECUDA;

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Fused unpack+FFT (PA_FFT_FORWARD) against the unfused pair it replaces:
+transpose! (K3) followed by a batched 1-d FFT along the new contiguous dim
+(cuFFT through torch.fft -- library code, the baseline).  One GPU, ComplexF64,
+CUDA events around back-to-back launches, arrays >> L2.
+
+  python profiles/prof_fft.py [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pencilarrays_b200 as pa  # noqa: E402
+
+PEAK = 6570.3
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timed(fn, reps=5):
+    for _ in range(2):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    topo = pa.MPITopology(pa.COMM_SELF, (1, 1))
+    rows = []
+    for dims in ((512, 512, 512), (256, 256, 256), (256, 1024, 256), (1024, 256, 256)):
+        px = pa.Pencil(topo, dims, (2, 3))
+        py = pa.Pencil(px, decomp_dims=(1, 3), permute=pa.Permutation(2, 1, 3))
+        pz = pa.Pencil(py, decomp_dims=(1, 2), permute=pa.Permutation(3, 2, 1))
+        ux, uy, uz = (pa.PencilArray.undef(torch.complex128, p) for p in (px, py, pz))
+        ux.data.view(torch.float64).normal_()
+        uy.data.view(torch.float64).normal_()
+        nb = 2 * ux.data.numel() * 16
+        for leg, dst, src in (("x->y", uy, ux), ("y->z", uz, uy)):
+            t = pa.Transposition(dst, src)
+            L = dst.data.shape[-1]
+            tmp = torch.empty_like(dst.data)
+            ms_t = timed(lambda: pa.transpose_(t))
+            ms_f = timed(lambda: torch.fft.fft(dst.data, dim=-1, out=tmp))
+            ms_tf = timed(lambda: (pa.transpose_(t), torch.fft.fft(dst.data, dim=-1, out=tmp)))
+            ms_fused = timed(lambda: pa.transpose_(t, fft="forward"))
+            r = dict(dims=dims, leg=leg, L=L, transpose_ms=round(ms_t, 4), cufft_ms=round(ms_f, 4),
+                     unfused_ms=round(ms_tf, 4), fused_ms=round(ms_fused, 4),
+                     fused_frac_of_hbm=round(nb / ms_fused / 1e6 / PEAK, 3),
+                     speedup_vs_unfused=round(ms_tf / ms_fused, 3))
+            rows.append(r)
+            print(r, flush=True)
+    if args.json:
+        json.dump(rows, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
