@@ -351,6 +351,32 @@ pa_status pa_host_chain_buffer(pa_host_chain* c, int slot, int which, void** dev
 pa_status pa_host_chain_time_begin(pa_host_chain* c);
 pa_status pa_host_chain_time_end(pa_host_chain* c, float* ms);
 
+/* ---- PencilIO binary layout ---------------------------------------
+ * Device arrays <-> the raw binary files of the reference's MPIIODriver
+ * (src/PencilIO/mpi_io.jl), byte for byte:
+ *   chunks == 0  the dataset is the GLOBAL array in the pencil's memory order, dims
+ *                (perm * size_global..., extra_dims...), column-major; this rank owns
+ *                the sub-box range_local(x, MemoryOrder()) (:372-380) -- files can be
+ *                read back with any other decomposition;
+ *   chunks != 0  the ranks' parent arrays one after the other in column-major order of
+ *                the process-grid coordinates (:382-424).
+ * `offset` = byte offset of the dataset in the file (MPIFile position, :159-164).
+ * Every rank calls these for its own part (no collective: ranks pwrite / pread
+ * disjoint byte ranges of the same file); the device array moves through a double-
+ * buffered pinned staging area.  The JSON sidecar (:194-211) is written by the host
+ * veneer (Julia: the reference's own add_metadata; Python mirror: pencilio.py).     */
+pa_status pa_io_sizes(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                      int chunks, int64_t* global_bytes, int64_t* local_bytes, int64_t* nruns,
+                      int64_t* run_bytes, int64_t* first_offset);
+/* the local array is `nruns` runs of `run_bytes` bytes, contiguous in the array and in the
+ * file; run r of the array starts `*file_offset` bytes into the dataset               */
+pa_status pa_io_run_offset(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                           int chunks, int64_t run, int64_t* file_offset);
+pa_status pa_io_write(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                      int chunks, const void* dev_array, const char* path, int64_t offset);
+pa_status pa_io_read(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                     int chunks, void* dev_array, const char* path, int64_t offset);
+
 /* CUDA-event timings (ms) of the last pa_transpose on this plan, named after
  * the reference's TimerOutputs sections (Transpositions.jl:172-175,326,336).
  * Blocks until that transpose has finished.                                  */

@@ -26,6 +26,10 @@ from .transpositions import (Transposition, transpose_, transpose_bang, Waitall,
                              Alltoallv, PeerPut, PeerGet, HostChain, transpose_host_, set_tunable)
 
 
+from . import pencilio as PencilIO
+from .pencilio import MPIIODriver, MPIFile, open_, read_, sizeof_global
+
+
 def launch_count() -> int:
     """Number of CUDA kernels libpa_b200 has launched in this process."""
     return int(lib.pa_launch_count())

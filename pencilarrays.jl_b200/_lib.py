@@ -128,6 +128,10 @@ SIGNATURES = {
     "pa_host_chain_time_begin": (C.c_int, [_P]),
     "pa_host_chain_time_end": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "pa_host_chain_buffer": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), _I64P]),
+    "pa_io_sizes": (C.c_int, [_P, C.c_int, _I64P, C.c_int, C.c_int, _I64P, _I64P, _I64P, _I64P, _I64P]),
+    "pa_io_run_offset": (C.c_int, [_P, C.c_int, _I64P, C.c_int, C.c_int, C.c_int64, _I64P]),
+    "pa_io_write": (C.c_int, [_P, C.c_int, _I64P, C.c_int, C.c_int, _P, C.c_char_p, C.c_int64]),
+    "pa_io_read": (C.c_int, [_P, C.c_int, _I64P, C.c_int, C.c_int, _P, C.c_char_p, C.c_int64]),
     "pa_plan_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "pa_plan_enable_timing": (C.c_int, [_P, C.c_int]),
 }

@@ -703,6 +703,41 @@ pa_status pa_host_chain_buffer(pa_host_chain* c, int slot, int which, void** dev
   return host_chain_buffer(c->p, slot, which, devptr, bytes);
 }
 
+// ---- PencilIO binary layout --------------------------------------------------------
+pa_status pa_io_sizes(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                      int chunks, int64_t* global_bytes, int64_t* local_bytes, int64_t* nruns,
+                      int64_t* run_bytes, int64_t* first_offset) {
+  GUARD({
+    if (!p || (n_extra > 0 && !extra_dims)) return PA_EINVAL;
+    return io_sizes(*p->p, n_extra, extra_dims, elsize, chunks, global_bytes, local_bytes, nruns,
+                    run_bytes, first_offset);
+  })
+}
+
+pa_status pa_io_run_offset(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                           int chunks, int64_t run, int64_t* file_offset) {
+  GUARD({
+    if (!p || !file_offset || (n_extra > 0 && !extra_dims)) return PA_EINVAL;
+    return io_run_offset(*p->p, n_extra, extra_dims, elsize, chunks, run, file_offset);
+  })
+}
+
+pa_status pa_io_write(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                      int chunks, const void* dev_array, const char* path, int64_t offset) {
+  GUARD({
+    if (!p || !path || offset < 0 || (n_extra > 0 && !extra_dims)) return PA_EINVAL;
+    return io_transfer(*p->p, n_extra, extra_dims, elsize, chunks, (void*)dev_array, path, offset, true);
+  })
+}
+
+pa_status pa_io_read(const pa_pencil* p, int n_extra, const int64_t* extra_dims, int elsize,
+                     int chunks, void* dev_array, const char* path, int64_t offset) {
+  GUARD({
+    if (!p || !path || offset < 0 || (n_extra > 0 && !extra_dims)) return PA_EINVAL;
+    return io_transfer(*p->p, n_extra, extra_dims, elsize, chunks, dev_array, path, offset, false);
+  })
+}
+
 pa_status pa_plan_timings(pa_plan* plan, pa_timings* t) {
   if (!plan || !t) return PA_EINVAL;
   return plan_timings(plan->p, t);

@@ -268,6 +268,14 @@ pa_status launch_flags(int n, unsigned long long* const* remote, unsigned long l
                        const unsigned long long* seq, bool do_signal, bool do_wait,
                        unsigned long long timeout_ns, int* err, void* stream);
 
+// PencilIO binary layout (io.cpp)
+pa_status io_sizes(const Pencil& P, int n_extra, const i64* extra, int elsize, int chunks,
+                   i64* global_bytes, i64* local_bytes, i64* nruns, i64* run_bytes, i64* first_offset);
+pa_status io_run_offset(const Pencil& P, int n_extra, const i64* extra, int elsize, int chunks, i64 run,
+                        i64* file_offset);
+pa_status io_transfer(const Pencil& P, int n_extra, const i64* extra, int elsize, int chunks, void* dev,
+                      const char* path, i64 offset, bool write);
+
 int device_count();
 pa_status set_device(int dev);
 i64 launch_count();
