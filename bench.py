@@ -810,14 +810,20 @@ def run_b200(args):
     houts = [torch.empty(ux.data.shape, dtype=dt).pin_memory() for _ in range(2)]
     e2e_steps = max(4, min(args.steps, 8))
     ets, _ = make_ts(name)
+    if args.host_slots:
+        pa.set_tunable("host_slots", args.host_slots)
+    if args.host_chunk_mib:
+        pa.set_tunable("host_chunk_bytes", args.host_chunk_mib << 20)
     hc = pa.HostChain(ets)  # collective for the one-sided methods (windows on the chain's buffers)
+    nfl = max(2, args.host_slots or 2)
+    houts = houts + [torch.empty(ux.data.shape, dtype=dt).pin_memory() for _ in range(nfl - 2)]
 
     def e2e_run(steps):
         tk = []
         for i in range(steps):
-            tk.append(hc.submit(hin, houts[i % 2]))
-            if i >= 1:
-                hc.wait(tk[i - 1])  # two submits in flight: download(i-1) || upload(i)
+            tk.append(hc.submit(hin, houts[i % nfl]))
+            if i >= nfl - 1:
+                hc.wait(tk[i - nfl + 1])  # `nfl` submits in flight: download(i-1) || upload(i)
         hc.wait()
 
     e2e_run(2)
@@ -950,6 +956,8 @@ def main():
     ap.add_argument("--only-default", action="store_true", help="N>1: skip the other methods")
     ap.add_argument("--all-variants", action="store_true", help="N>1: also the chunked / reordered variants")
     ap.add_argument("--variants", default=None, help="N>1: comma-separated indices of the method variants to run")
+    ap.add_argument("--host-slots", type=int, default=None, help="e2e: tunable host_slots (2..4)")
+    ap.add_argument("--host-chunk-mib", type=int, default=None, help="e2e: tunable host_chunk_bytes")
     ap.add_argument("--quick", action="store_true", help="skip the side measurements (kernels, configs[1])")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -68,6 +68,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   else if (!strcmp(name, "pdl")) g_tun.pdl = (int)value;
   else if (!strcmp(name, "nccl_ctas")) g_tun.nccl_ctas = (int)value;
   else if (!strcmp(name, "host_chunk_bytes")) g_tun.host_chunk_bytes = value;
+  else if (!strcmp(name, "host_slots")) g_tun.host_slots = (int)value;
   else {
     set_error("unknown tunable '%s'", name);
     return PA_EINVAL;

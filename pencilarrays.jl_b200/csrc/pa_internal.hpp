@@ -172,6 +172,7 @@ struct Tunables {
   int pdl = 1;           // programmatic dependent launch between the back-to-back kernels of a chain
   int nccl_ctas = 0;     // > 0: ncclCommInitRankConfig min/maxCTAs
   long long host_chunk_bytes = 64ll << 20;  // pa_transpose_host: bytes per pipelined chunk
+  int host_slots = 2;    // pa_host_chain: device staging sets = submits that may be in flight (2..4)
 };
 extern Tunables g_tun;
 

@@ -1307,23 +1307,23 @@ pa_status transpose_host(Plan* P, Comm* comm, const void* hsrc, void* hdst, unsi
 struct HostChain {
   std::vector<Plan*> plans;
   Comm* comm = nullptr;
-  static constexpr int SLOTS = 2;
-  void* buf[SLOTS][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  static constexpr int MAX_SLOTS = 4;
+  int SLOTS = 2;  // device staging sets: submits that may be in flight at once (tunable "host_slots")
+  void* buf[MAX_SLOTS][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
   i64 cap = 0;
   cudaStream_t h2d_s = nullptr, ks = nullptr, d2h_s = nullptr;
-  cudaEvent_t ev_up[SLOTS] = {nullptr, nullptr}, ev_k[SLOTS] = {nullptr, nullptr},
-              ev_out[SLOTS] = {nullptr, nullptr};
-  std::vector<cudaEvent_t> evs[SLOTS], evs_last[SLOTS];
+  cudaEvent_t ev_up[MAX_SLOTS] = {nullptr}, ev_k[MAX_SLOTS] = {nullptr}, ev_out[MAX_SLOTS] = {nullptr};
+  std::vector<cudaEvent_t> evs[MAX_SLOTS], evs_last[MAX_SLOTS];
   cudaEvent_t t_mark = nullptr, t_end = nullptr;  // device-side timing of a run of submits
   HostCuts first, last;
   i64 submitted = 0;
-  i64 ticket_of[SLOTS] = {-1, -1};
+  i64 ticket_of[MAX_SLOTS] = {-1, -1, -1, -1};
 };
 
 void host_chain_destroy(HostChain* c) {
   if (!c) return;
   cudaDeviceSynchronize();
-  for (int s = 0; s < HostChain::SLOTS; ++s) {
+  for (int s = 0; s < HostChain::MAX_SLOTS; ++s) {
     for (int k = 0; k < 2; ++k)
       if (c->buf[s][k]) cudaFree(c->buf[s][k]);
     for (cudaEvent_t e : {c->ev_up[s], c->ev_k[s], c->ev_out[s]})
@@ -1377,13 +1377,14 @@ pa_status host_chain_create(int n, Plan* const* plans, Comm* comm, HostChain** o
   }
   c->comm = comm;
   c->cap = std::max<i64>(c->cap, 1);
+  c->SLOTS = std::max(2, std::min(g_tun.host_slots, (int)HostChain::MAX_SLOTS));
   HostChain* raw = c.get();
   auto fail = [&](pa_status s) {
     host_chain_destroy(c.release());
     return s;
   };
   (void)raw;
-  for (int s = 0; s < HostChain::SLOTS; ++s)
+  for (int s = 0; s < c->SLOTS; ++s)
     for (int k = 0; k < 2; ++k)
       if (cudaMalloc(&c->buf[s][k], (size_t)c->cap) != cudaSuccess) {
         set_error("host chain: device staging allocation failed");
@@ -1392,7 +1393,7 @@ pa_status host_chain_create(int n, Plan* const* plans, Comm* comm, HostChain** o
       }
   for (cudaStream_t* s : {&c->h2d_s, &c->ks, &c->d2h_s})
     if (cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess) return fail(PA_ECUDA);
-  for (int s = 0; s < HostChain::SLOTS; ++s)
+  for (int s = 0; s < c->SLOTS; ++s)
     for (cudaEvent_t* e : {&c->ev_up[s], &c->ev_k[s], &c->ev_out[s]})
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail(PA_ECUDA);
   c->first = make_cuts(c->plans.front(), g_tun.host_chunk_bytes);
@@ -1403,7 +1404,12 @@ pa_status host_chain_create(int n, Plan* const* plans, Comm* comm, HostChain** o
 }
 
 pa_status host_chain_buffer(HostChain* c, int slot, int which, void** p, i64* bytes) {
-  if (slot < 0 || slot >= HostChain::SLOTS || which < 0 || which > 1) return PA_EINVAL;
+  if (slot < 0 || slot >= HostChain::MAX_SLOTS || which < 0 || which > 1) return PA_EINVAL;
+  if (slot >= c->SLOTS) {
+    if (p) *p = nullptr;
+    if (bytes) *bytes = 0;
+    return PA_OK;
+  }
   if (p) *p = c->buf[slot][which];
   if (bytes) *bytes = c->cap;
   return PA_OK;
@@ -1411,7 +1417,7 @@ pa_status host_chain_buffer(HostChain* c, int slot, int which, void** p, i64* by
 
 pa_status host_chain_submit(HostChain* c, const void* hsrc, void* hdst, i64* ticket) {
   const int n = (int)c->plans.size();
-  const int slot = (int)(c->submitted % HostChain::SLOTS);
+  const int slot = (int)(c->submitted % c->SLOTS);
   Plan* P0 = c->plans.front();
   Plan* Pl = c->plans.back();
   const i64 nin = P0->length_in * P0->elsize, nout = Pl->length_out * Pl->elsize;
@@ -1479,12 +1485,11 @@ pa_status host_chain_submit(HostChain* c, const void* hsrc, void* hdst, i64* tic
 }
 
 pa_status host_chain_wait(HostChain* c, i64 ticket) {
-  for (int s = 0; s < HostChain::SLOTS; ++s) {
+  for (int s = 0; s < c->SLOTS; ++s) {
     if (c->ticket_of[s] < 0) continue;
     if (ticket >= 0 && c->ticket_of[s] > ticket) continue;  // a later submit: not asked for
     CU(cudaEventSynchronize(c->ev_out[s]));
   }
-  if (ticket >= 0 && ticket < c->submitted - HostChain::SLOTS) return PA_OK;  // long gone
   return PA_OK;
 }
 

@@ -115,8 +115,34 @@ function handles(topo)
         check(ccall((:pa_set_device, libpa), Cint, (Cint,), CUDA.deviceid(CUDA.device())))
         check(ccall((:pa_comm_init_rank, libpa), Cint, (Ptr{UInt8}, Cint, Cint, Ptr{Ptr{Cvoid}}),
                     id, MPI.Comm_size(get_comm(topo)), rank, c))
+        setup_flag_window!(c[], get_comm(topo))
         Handles(h[], IdDict{Any,Ptr{Cvoid}}(), Dict{Any,Ptr{Cvoid}}(), c[])
     end
+end
+
+# Flag window of the one-sided methods (pa_comm_flags_export / _import): every rank
+# exports a few 64-bit words per source rank and maps everybody else's; window-open /
+# window-close of PeerPut / PeerGet then ride inside the transfer kernel as NVLink
+# signals.  Collective; if ANY rank fails, all keep the NCCL fences.
+function setup_flag_window!(comm_handle::Ptr{Cvoid}, comm::MPI.Comm)
+    rank, nranks = MPI.Comm_rank(comm), MPI.Comm_size(comm)
+    handle = zeros(UInt8, 64)
+    off = Ref{Int64}(0)
+    ok = ccall((:pa_comm_flags_export, libpa), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int64}),
+               comm_handle, handle, off) == 0
+    handles_all = MPI.Allgather(handle, comm)
+    offs_all = MPI.Allgather([off[]], comm)
+    ok = MPI.Allreduce(ok, &, comm)
+    if ok
+        for r in 0:(nranks - 1)
+            r == rank && continue
+            ok &= ccall((:pa_comm_flags_import, libpa), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}, Int64),
+                        comm_handle, r, view(handles_all, 64r+1:64r+64), offs_all[r + 1]) == 0
+        end
+    end
+    MPI.Allreduce(ok, &, comm) ||
+        check(ccall((:pa_set_tunable, libpa), Cint, (Cstring, Int64), "nccl_fences", 1))
+    nothing
 end
 
 function pencil_handle(H::Handles, p::Pencil{N}) where {N}
@@ -176,6 +202,8 @@ function register_window!(t::Transposition)
                     view(handles_all, 64r+1:64r+64), offs_all[r + 1], mapped))
         check(ccall((:pa_plan_set_window, libpa), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
                     plan, devptr(A), n, mapped[]))
+        # (each import holds a reference on the mapping: pair it with pa_ipc_release(handle)
+        #  when the window array is freed)
     end
     t
 end
@@ -198,15 +226,71 @@ end
 const DeviceTransposition{T,N} = Transposition{T,N,<:Pencil,<:Pencil,
     <:PencilArray{T,N,<:CuArray},<:PencilArray{T,N,<:CuArray}}
 
-# transpose!(t; waitall) (Transpositions.jl:170-179)
-function Transpositions.transpose!(t::DeviceTransposition; waitall = true)
+# transpose!(t; waitall) (Transpositions.jl:170-179).
+# `fft = :forward | :backward` (B200 extension, PA_FFT_FORWARD / PA_FFT_BACKWARD): the unpack
+# and the 1-d FFT along dest's contiguous dimension -- the next step of a PencilFFTs plan --
+# run as ONE kernel (ComplexF64, power-of-two lines of 8..1024 points, staged methods).
+function Transpositions.transpose!(t::DeviceTransposition; waitall = true, fft = nothing)
     plan, H = plan_handle(t)
     flags = waitall ? Cuint(1) : Cuint(0)        # PA_WAITALL
+    fft === :forward && (flags |= Cuint(8))
+    fft === :backward && (flags |= Cuint(16))
+    ptr_or_null(A) = isempty(A) ? C_NULL : devptr(A)   # a rank may own nothing (Pencils.jl:193-218)
     check(ccall((:pa_transpose, libpa), Cint,
         (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cuint, Ptr{Cvoid}),
-        plan, H.comm, devptr(parent(t.Ai)), devptr(parent(t.Ao)), flags, stream_ptr()))
+        plan, H.comm, ptr_or_null(parent(t.Ai)), ptr_or_null(parent(t.Ao)), flags, stream_ptr()))
     t
 end
+
+# ---- host arrays: a chain of transpositions on `Array`-backed data ------------------
+# pa_host_chain_*: one submit = upload, every transpose! on the device, download;
+# asynchronous, double-buffered (download of one submit || upload of the next).
+mutable struct HostChain
+    h::Ptr{Cvoid}
+end
+function HostChain(ts::Vector{<:Transposition})
+    plans = Ptr{Cvoid}[plan_handle(t)[1] for t in ts]
+    H = handles(first(ts).Pi.topology)
+    h = Ref{Ptr{Cvoid}}()
+    check(ccall((:pa_host_chain_create, libpa), Cint, (Cint, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
+                length(plans), plans, H.comm, h))
+    finalizer(c -> ccall((:pa_host_chain_destroy, libpa), Cvoid, (Ptr{Cvoid},), c.h), HostChain(h[]))
+end
+function submit!(c::HostChain, host_dst::Array, host_src::Array)   # pin both with CUDA.pin
+    k = Ref{Int64}(0)
+    check(ccall((:pa_host_chain_submit, libpa), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}),
+                c.h, pointer(host_src), pointer(host_dst), k))
+    k[]
+end
+Base.wait(c::HostChain, ticket = -1) =
+    check(ccall((:pa_host_chain_wait, libpa), Cint, (Ptr{Cvoid}, Int64), c.h, ticket))
+
+# ---- PencilIO: MPIIODriver files straight from / into device arrays ------------------
+# The reference's set_view! + MPI.File.write_all (mpi_io.jl:338-380) needs host memory;
+# these methods keep its file format (and its own add_metadata / JSON sidecar) and move
+# the rank's sub-box with pa_io_write / pa_io_read.
+using PencilArrays.PencilIO: PencilIO
+function PencilIO.write_discontiguous(ff::MPI.FileHandle, x::PencilArray{T,N,<:CuArray};
+                                      offset, collective, filename, infokws...) where {T,N}
+    H = handles(topology(pencil(x)))
+    ex = Int64[extra_dims(x)...]
+    check(ccall((:pa_io_write, libpa), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Cstring, Int64),
+        pencil_handle(H, pencil(x)), length(ex), ex, sizeof(T), 0, devptr(parent(x)), filename, offset))
+    nothing
+end
+function PencilIO.read_discontiguous!(ff::MPI.FileHandle, x::PencilArray{T,N,<:CuArray};
+                                      offset, collective, filename, infokws...) where {T,N}
+    H = handles(topology(pencil(x)))
+    ex = Int64[extra_dims(x)...]
+    check(ccall((:pa_io_read, libpa), Cint,
+        (Ptr{Cvoid}, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Cstring, Int64),
+        pencil_handle(H, pencil(x)), length(ex), ex, sizeof(T), 0, devptr(parent(x)), filename, offset))
+    x
+end
+# (the chunks = true pair, write_contiguous / read_contiguous!, passes 1 instead of 0; the
+#  caller supplies `filename = get_filename(file)` -- two one-line forwarding methods of
+#  setindex!(::MPIFile, …) / _read_mpiio! in the extension)
 
 # MPI.Waitall(t) (Transpositions.jl:127-130)
 function MPI.Waitall(t::DeviceTransposition)

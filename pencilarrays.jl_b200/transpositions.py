@@ -361,7 +361,11 @@ class HostChain:
         _stream_ptr()
         check(lib.pa_host_chain_create(n, arr, comm.handle, C.byref(h)))
         self.h = h
-        for slot in range(2):
+        for slot in range(4):
+            probe = C.c_void_p()
+            check(lib.pa_host_chain_buffer(h, slot, 0, C.byref(probe), None))
+            if not probe.value:
+                break  # the chain has fewer staging sets (tunable "host_slots")
             for i, t in enumerate(ts):
                 info = t.plan.info
                 if info.dim == 0 or info.nproc == 1 or comm.handle is None:
