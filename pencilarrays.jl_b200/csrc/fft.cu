@@ -13,8 +13,10 @@
 //     peers sent (dense in recv_buf, wire layout of :380-416) and the self block
 //     straight out of `src` -- with 128-byte (8 x ComplexF64) coalesced loads,
 //     writing them transposed into shared memory (padded: fft_core.hpp);
-//   * runs the mixed-radix (2/4/8) decimation-in-frequency passes in shared
-//     memory, butterflies in registers;
+//   * runs the mixed-radix (2/4/8) decimation-in-frequency passes in shared memory,
+//     butterflies in registers; for 1024-point lines the first pass (radix 16) runs on
+//     the values as they arrive from HBM -- a thread's loads are exactly one
+//     butterfly's inputs -- before they ever touch shared memory;
 //   * stores each transformed line with fully contiguous 128-bit stores.
 //
 // HBM traffic: 2 * s * n bytes for n elements, the same as the plain unpack.
@@ -130,31 +132,68 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
   const int ncol = (int)((p.ex - x0) < C ? (p.ex - x0) : C);
   const int pitch = p.pitch;
 
-  // ---- gather: C threads read C consecutive columns (C x 16 B) of one source row;
-  //      8 rows in flight per thread ----
+  // ---- gather (+ first pass): C threads read C consecutive columns (C x 16 B) of one
+  //      source row.  A thread owns the rows r, r + RS, r + 2 RS, ... of its column: exactly
+  //      the inputs of one butterfly of a first pass of radix R1 = L / RS -- so that pass runs
+  //      on the values as they arrive from HBM, before they ever touch shared memory ----
+  constexpr int RS = FFT_THREADS / C;  // rows per sweep
+  constexpr int LOGRS = (C == 8) ? 5 : 6;
+  static_assert((1 << LOGRS) == RS, "rows per sweep");
+  // (measured on B200, profiles/r2_fused_fft.txt: a win for 1024-point lines -- one CTA
+  //  per SM less bound by shared memory --, a loss for 512-point lines, where the radix-16
+  //  butterfly's 126 registers cost the third resident CTA: 1.17 -> 1.45 ms at 512^3)
+  constexpr int LOGR1 = (LOGL == 10) ? (LOGL - LOGRS) : 0;
+  static_assert(LOGR1 == 0 || LOGL - LOGR1 == LOGRS, "first-pass stride must equal the sweep");
+  const cplx* twp = p.tw;
+  auto tw = [twp](int i) {
+    const double2 w = __ldg(reinterpret_cast<const double2*>(twp) + i);
+    return cplx{w.x, w.y};
+  };
   {
     const int c = t % C, r = t / C;
-    constexpr int RS = FFT_THREADS / C;  // rows per sweep
-    constexpr int U = 8;
     cplx* line = sm + c * pitch;
+    if constexpr (LOGR1 > 0) {
+      constexpr int R1 = 1 << LOGR1;
+      if (c < ncol) {
+        double2 v[R1];
 #pragma unroll
-    for (int b = 0; b < FFT_MAXB; ++b) {
-      if (b < p.nb) {
-        const FftBlock& B = p.blk[b];
-        const char* s = B.src + so_off[b] + (x0 + c) * (long long)sizeof(cplx);
-        const int ey = B.ey, y0 = B.y0;
-        const long long ssy = B.ssy;
-        for (int y = r; y < ey; y += U * RS) {
-          double2 v[U];
+        for (int q = 0; q < R1; ++q) {
+          const int y = r + q * RS;
+          const char* s = nullptr;
 #pragma unroll
-          for (int k = 0; k < U; ++k) {
-            const int yy = y + k * RS;
-            if (c < ncol && yy < ey) v[k] = __ldcs(reinterpret_cast<const double2*>(s + (long long)yy * ssy));
-          }
+          for (int b = 0; b < FFT_MAXB; ++b)
+            if (b < p.nb && y >= p.blk[b].y0 && y < p.blk[b].y0 + p.blk[b].ey)
+              s = p.blk[b].src + so_off[b] + (long long)(y - p.blk[b].y0) * p.blk[b].ssy;
+          v[q] = __ldcs(reinterpret_cast<const double2*>(s + (x0 + c) * (long long)sizeof(cplx)));
+        }
+        cplx a[R1];
 #pragma unroll
-          for (int k = 0; k < U; ++k) {
-            const int yy = y + k * RS;
-            if (c < ncol && yy < ey) line[pa_fft::pad_index(y0 + yy)] = cplx{v[k].x, v[k].y};
+        for (int q = 0; q < R1; ++q) a[q] = cplx{v[q].x, v[q].y};
+        pa_fft::butterfly_regs<R1>(a, r, L, L, p.sign, tw);
+#pragma unroll
+        for (int q = 0; q < R1; ++q) line[pa_fft::pad_index(r + q * RS)] = a[q];
+      }
+    } else {
+      constexpr int U = 8;
+#pragma unroll
+      for (int b = 0; b < FFT_MAXB; ++b) {
+        if (b < p.nb) {
+          const FftBlock& B = p.blk[b];
+          const char* s = B.src + so_off[b] + (x0 + c) * (long long)sizeof(cplx);
+          const int ey = B.ey, y0 = B.y0;
+          const long long ssy = B.ssy;
+          for (int y = r; y < ey; y += U * RS) {
+            double2 v[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              const int yy = y + k * RS;
+              if (c < ncol && yy < ey) v[k] = __ldcs(reinterpret_cast<const double2*>(s + (long long)yy * ssy));
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+              const int yy = y + k * RS;
+              if (c < ncol && yy < ey) line[pa_fft::pad_index(y0 + yy)] = cplx{v[k].x, v[k].y};
+            }
           }
         }
       }
@@ -162,13 +201,8 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
   }
   __syncthreads();
 
-  // ---- passes (radices and strides are compile-time constants) ----
-  const cplx* twp = p.tw;
-  auto tw = [twp](int i) {
-    const double2 w = __ldg(reinterpret_cast<const double2*>(twp) + i);
-    return cplx{w.x, w.y};
-  };
-  fft_passes<LOGL, LOGL, C>(sm, pitch, ncol, p.sign, tw);
+  // ---- remaining passes in shared memory (radices and strides are compile-time constants) ----
+  fft_passes<LOGL, LOGL - LOGR1, C>(sm, pitch, ncol, p.sign, tw);
 
   // ---- store: natural order, every line one contiguous run ----
   char* d = p.dst + x0 * p.dsx + d_off;
@@ -179,7 +213,10 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
     for (int k0 = 0; k0 < L; k0 += FFT_THREADS) {
       const int k = k0 + t;
       if (k < L) {
-        const cplx v = line[pa_fft::pad_index(fft_pos<LOGL, LOGL>(k))];
+        // position of frequency k: first-pass digit, then the digits of the later passes
+        const int pos = ((k & ((1 << LOGR1) - 1)) << (LOGL - LOGR1)) +
+                        fft_pos<LOGL, LOGL - LOGR1>(k >> LOGR1);
+        const cplx v = line[pa_fft::pad_index(pos)];
         __stcs(out + k, make_double2(v.x, v.y));
       }
     }

@@ -66,6 +66,16 @@ PA_HD Radices radices_of(int logL) {
   return R;
 }
 
+// same, with a given first radix (the fused kernel's in-register first pass)
+PA_HD Radices radices_with_first(int logL, int logR1) {
+  Radices R;
+  R.n = 0;
+  if (logR1 > 0) R.r[R.n++] = 1 << logR1;
+  const Radices rest = radices_of(logL - logR1);
+  for (int i = 0; i < rest.n; ++i) R.r[R.n++] = rest.r[i];
+  return R;
+}
+
 // position (after all passes) of output frequency k
 PA_HD int fft_position_of(int k, int L, const Radices& R) {
   int p = 0, stride = L;
@@ -112,6 +122,94 @@ PA_HD void dft8(cplx* a, int sign) {
   }
 }
 
+// 16 = 4 x 4: a[4*q1 + q2] -> A[s1 + 4*s2]
+PA_HD void dft16(cplx* a, int sign) {
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos, sin(pi/8)
+  const double h = 0.70710678118654752440;
+  cplx b[4][4];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q2 = 0; q2 < 4; ++q2) {
+    cplx t[4] = {a[q2], a[4 + q2], a[8 + q2], a[12 + q2]};
+    dft4(t, sign);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) b[q2][k] = t[k];
+  }
+  // b[q2][s1] *= w16^(q2*s1), w16 = exp(sign*i*pi/8)
+  const cplx w1 = cplx{c1, sign * s1}, w2 = cplx{h, sign * h}, w3 = cplx{s1, sign * c1};
+  const cplx w6 = cplx{-h, sign * h}, w9 = cplx{-c1, -sign * s1};
+  b[1][1] = cmul(b[1][1], w1);
+  b[1][2] = cmul(b[1][2], w2);
+  b[1][3] = cmul(b[1][3], w3);
+  b[2][1] = cmul(b[2][1], w2);
+  b[2][2] = mul_i(b[2][2], sign);   // w4 = sign*i
+  b[2][3] = cmul(b[2][3], w6);
+  b[3][1] = cmul(b[3][1], w3);
+  b[3][2] = cmul(b[3][2], w6);
+  b[3][3] = cmul(b[3][3], w9);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 4; ++k) {
+    cplx t[4] = {b[0][k], b[1][k], b[2][k], b[3][k]};
+    dft4(t, sign);
+    a[k] = t[0];
+    a[k + 4] = t[1];
+    a[k + 8] = t[2];
+    a[k + 12] = t[3];
+  }
+}
+
+// the R-1 twiddles W^(step*s), s = 1..R-1, of one butterfly from the table entries at
+// step, 2 step, 4 step (and 8 step): the others are one or two complex products away
+template <int R, class Tw>
+PA_HD void butterfly_twiddles(cplx* w, int step, int L, int sign, const Tw& tw) {
+  w[1] = tw(step & (L - 1));
+  if (R > 2) w[2] = tw((2 * step) & (L - 1));
+  if (R > 4) w[4] = tw((4 * step) & (L - 1));
+  if (R > 8) w[8] = tw((8 * step) & (L - 1));
+  if (sign > 0) {
+    w[1].y = -w[1].y;
+    if (R > 2) w[2].y = -w[2].y;
+    if (R > 4) w[4].y = -w[4].y;
+    if (R > 8) w[8].y = -w[8].y;
+  }
+  if (R > 2) w[3] = cmul(w[1], w[2]);
+  if (R > 4) {
+    w[5] = cmul(w[4], w[1]);
+    w[6] = cmul(w[4], w[2]);
+    w[7] = cmul(w[4], w[3]);
+  }
+  if (R > 8) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int s = 1; s < 8; ++s) w[8 + s] = cmul(w[8], w[s]);
+  }
+}
+
+// The R-point transform + twiddles of one butterfly on values already in registers
+// (the fused kernel's first pass works on the rows it has just loaded from HBM).
+template <int R, class Tw>
+PA_HD void butterfly_regs(cplx* a, int j, int L, int M, int sign, const Tw& tw) {
+  if (R == 2) dft2(a);
+  if (R == 4) dft4(a, sign);
+  if (R == 8) dft8(a, sign);
+  if (R == 16) dft16(a, sign);
+  const int step = j * (L / M);   // W_M^(j*s) = W_L^(j*s*L/M)
+  if (step > 0) {
+    cplx w[R > 1 ? R : 2];
+    butterfly_twiddles<R>(w, step, L, sign, tw);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int s = 1; s < R; ++s) a[s] = cmul(a[s], w[s]);
+  }
+}
+
 // One butterfly `u` (< L/R) of a pass with radix R over sub-length M on one line.
 // x.get / x.put map a logical position to the (padded) storage; tw(i) = forward table
 // entry W_L^i.  Only W^step, W^(2 step) and W^(4 step) are looked up: the other four
@@ -128,31 +226,7 @@ PA_HD void butterfly(Line& x, int u, int L, int M, int sign, const Tw& tw) {
 #pragma unroll
 #endif
   for (int q = 0; q < R; ++q) a[q] = x.get(base + q * Q);
-  if (R == 2) dft2(a);
-  if (R == 4) dft4(a, sign);
-  if (R == 8) dft8(a, sign);
-  const int step = j * (L / M);   // W_M^(j*s) = W_L^(j*s*L/M)
-  if (step > 0) {
-    cplx w[R > 1 ? R : 2];
-    w[1] = tw(step & (L - 1));
-    if (R > 2) w[2] = tw((2 * step) & (L - 1));
-    if (R > 4) w[4] = tw((4 * step) & (L - 1));
-    if (sign > 0) {
-      w[1].y = -w[1].y;
-      if (R > 2) w[2].y = -w[2].y;
-      if (R > 4) w[4].y = -w[4].y;
-    }
-    if (R > 2) w[3] = cmul(w[1], w[2]);
-    if (R > 4) {
-      w[5] = cmul(w[4], w[1]);
-      w[6] = cmul(w[4], w[2]);
-      w[7] = cmul(w[4], w[3]);
-    }
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int s = 1; s < R; ++s) a[s] = cmul(a[s], w[s]);
-  }
+  butterfly_regs<R>(a, j, L, M, sign, tw);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif

@@ -1,7 +1,8 @@
 // CPU run of the shared FFT core (pencilarrays.jl_b200/csrc/fft_core.hpp): the same
 // radix plan, butterflies, padded indexing and digit-reversed read-out the CUDA kernel
 // executes.  TEST INFRASTRUCTURE -- not linked into libpa_b200, never used by the product.
-//   fft_host_check L sign < in.bin > out.bin      (L complex doubles each way)
+//   fft_host_check L sign [logR1] < in.bin > out.bin      (L complex doubles each way;
+//   logR1 > 0: first pass of radix 2^logR1 on register values, like the kernel's gather)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +32,8 @@ int main(int argc, char** argv) {
   }
   Line x{buf.data()};
   for (int i = 0; i < L; ++i) x.put(i, in[i]);
-  const Radices R = radices_of(logL);
+  const int logR1 = argc > 3 ? atoi(argv[3]) : 0;
+  const Radices R = logR1 > 0 ? radices_with_first(logL, logR1) : radices_of(logL);
   auto twf = [&](int i) { return tw[i]; };
   int M = L;
   for (int pss = 0; pss < R.n; ++pss) {
@@ -40,6 +42,7 @@ int main(int argc, char** argv) {
       if (r == 2) butterfly<2>(x, u, L, M, sign, twf);
       if (r == 4) butterfly<4>(x, u, L, M, sign, twf);
       if (r == 8) butterfly<8>(x, u, L, M, sign, twf);
+      if (r == 16) butterfly<16>(x, u, L, M, sign, twf);
     }
     M /= r;
   }

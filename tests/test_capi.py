@@ -143,3 +143,38 @@ def test_python_mirror_geometry_matches_docs():
     assert pa.to_local(p, (range(3, 5), range(16, 18), range(21, 30))) == (range(3, 5), range(1, 3), range(2, 11))
     assert pa.range_remote(p, (3, 3)) == pa.range_local(p)
     assert pa.length_global(p) == 42 * 31 * 29
+
+
+def test_non_power_of_two_elements_cost_one_dimension():
+    """A 12- or 24-byte element moves as several words through an extra innermost
+    dimension: N + n_extra == PA_MAX_DIMS then no longer fits and must be refused, not
+    overflow the descriptors."""
+    topo = pa.MPITopology(pa.Comm(0, 2), (2,))
+    dims = (4, 3, 2, 2, 2)
+    px = pa.Pencil(topo, dims, (5,))
+    py = pa.Pencil(px, decomp_dims=(4,))
+    for extra, elsize, ok in [((2, 2, 2), 8, True), ((2, 2, 2), 12, False), ((2, 2), 24, True),
+                              ((2, 2, 2), 48, False), ((2, 2, 2), 16, True)]:
+        h = C.c_void_p()
+        st = lib.pa_plan_create(px._h, py._h, len(extra), i64arr(extra), elsize, 0, C.byref(h))
+        assert (st == _lib.PA_OK) == ok, (extra, elsize, lib.pa_last_error())
+        if ok:
+            lib.pa_plan_destroy(h)
+
+
+def test_new_entry_points_refuse_without_gpu_or_bad_arguments():
+    assert lib.pa_set_tunable(b"fence_timeout_ms", 1000) == _lib.PA_OK
+    assert lib.pa_set_tunable(b"fence_timeout_ms", 60000) == _lib.PA_OK
+    assert lib.pa_set_tunable(b"no_such_tunable", 1) == _lib.PA_EINVAL
+    h = C.c_void_p()
+    assert lib.pa_comm_init_local(0, 0, C.byref(h)) == _lib.PA_EINVAL
+    assert lib.pa_host_chain_create(0, None, None, C.byref(h)) == _lib.PA_EINVAL
+    if lib.pa_device_count() == 0:
+        assert lib.pa_comm_init_local(2, 0, C.byref(h)) == _lib.PA_ENOGPU
+        topo = pa.MPITopology(pa.COMM_SELF, (1, 1))
+        p = pa.Pencil(topo, (4, 4, 4), (2, 3))
+        assert lib.pa_io_write(p._h, 0, None, 8, 0, None, b"/tmp/x.bin", 0) == _lib.PA_ENOGPU
+        # the layout arithmetic itself is host code
+        gb = C.c_int64()
+        assert lib.pa_io_sizes(p._h, 0, None, 8, 0, C.byref(gb), None, None, None, None) == _lib.PA_OK
+        assert gb.value == 4 * 4 * 4 * 8

@@ -91,8 +91,9 @@ def test_c_port_equals_numpy_oracle(case):
 
 def test_golden_fixtures():
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from this
-    oracle at commit time; they freeze its behaviour (regression pin) and are
-    what the GPU parity tests also compare against."""
+    oracle at commit time; they freeze its behaviour (regression pin); the GPU path is
+    compared against the same files in tests/test_gpu_transpose.py::
+    test_gpu_path_against_committed_golden_fixtures."""
     files = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz"))
     assert files, "golden fixtures missing"
     for f in files:
