@@ -200,6 +200,44 @@ def main():
                 got = A[3].data.view(torch.uint8).reshape(-1).cpu().numpy()
                 want = np.ascontiguousarray(o2[rank].data.reshape(-1, order="F")).view(np.uint8)
                 assert got.tobytes() == want.tobytes(), ("inplace", case["name"], rank, method)
+    if mode != "gloo":
+        # PencilIO with REAL ranks writing one file concurrently (mpi_io.jl layout): every rank
+        # pwrite()s its sub-box, rank 0 checks the bytes against the gathered global array and
+        # everybody reads its part back (test/io.jl:28-105)
+        for case in [c for c in CASES if math.prod(c["grid"]) == world and c["it"] in (4, 8, 16)][:2]:
+            dtype, it, extra = DTYPES[case["it"]], case["it"], case["extra"]
+            tdt = {4: torch.float32, 8: torch.float64, 16: torch.complex128}[it]
+            decomp, perm = case["chain"][1]
+            topo = pa.MPITopology(comm, case["grid"])
+            pen = pa.Pencil(topo, case["dims"], decomp, permute=perm_of(perm))
+            open_ = [O.OPencil(O.OTopology(case["grid"], r), case["dims"], decomp, perm) for r in range(world)]
+            g = O.global_pattern(case["dims"], extra, it)
+            mine = O.scatter(g, open_, extra, dtype)[rank]
+            u = pa.PencilArray.undef(tdt, pen, *extra)
+            u.data.view(torch.uint8).reshape(-1).copy_(torch.from_numpy(
+                np.ascontiguousarray(mine.data.reshape(-1, order="F")).view(np.uint8).copy()))
+            fname = f"/tmp/pa_io_{os.environ.get('MASTER_PORT', '0')}_{case['name']}.bin"
+            with pa.open_(pa.MPIIODriver(), fname, comm, write=True, create=True) as ff:
+                ff.write("u", u, chunks=False)
+                ff.write("u_chunks", u, chunks=True)
+            if rank == 0:
+                nd = len(case["dims"])
+                axes = tuple(range(nd)) if perm is None else tuple(q - 1 for q in perm)
+                gl = np.transpose(g, axes + tuple(range(nd, g.ndim)))  # memory order + extra + bytes
+                want = np.ascontiguousarray(gl.reshape(-1, it, order="F")).tobytes()
+                raw = open(fname, "rb").read()
+                assert raw[:len(want)] == want, ("pencilio layout", case["name"])
+                assert len(raw) == 2 * len(want)
+            for name in ("u", "u_chunks"):
+                v = pa.PencilArray.undef(tdt, pen, *extra)
+                v.data.view(torch.uint8).fill_(0x11)
+                with pa.open_(pa.MPIIODriver(), fname, comm, read=True) as ff:
+                    pa.read_(ff, v, name)
+                assert torch.equal(v.data.view(torch.uint8), u.data.view(torch.uint8)), ("pencilio", name)
+            dist.barrier()
+            if rank == 0:
+                os.remove(fname)
+                os.remove(fname + ".json")
     dist.barrier()
     if rank == 0:
         print(f"MP_WORKER_OK mode={mode} world={world} cases={ran} launches={pa.launch_count()}")
