@@ -694,16 +694,21 @@ def run_b200(args):
                     ("pointtopoint", {"ipc_exchange": 1}),
                     ("pointtopoint", {"ipc_exchange": 1, "p2p_chunks": 4}),
                     ("alltoallv", {"ipc_exchange": 1}),
-                    ("peerput", {"multi_put": 0})]
+                    ("peerput", {"multi_put": 0}),
+                    ("peerput", {"oneside_self_ctas": -1}), ("peerput", {"oneside_self_ctas": -2}),
+                    ("peerput", {"remote_ctas": -8}), ("peerput", {"remote_ctas": -2}),
+                    ("peerput", {"remote_ctas": -8, "oneside_self_ctas": -2})]
         if args.variants:
             variants = [v for i, v in enumerate(variants) if str(i) in args.variants.split(",")]
         elif not args.all_variants:
             # (chunked NCCL sends cost ~0.1 ms per operation: 2-3x slower at N=8, measured in
             #  profiles/r2_bench_n8.json -- kept out of the default run)
-            variants = [v for v in variants if "p2p_chunks" not in v[1] and "self_first" not in v[1]]
+            variants = [v for v in variants if not (set(v[1]) & {"p2p_chunks", "self_first", "remote_ctas",
+                                                                  "oneside_self_ctas"})]
         defaults = {"p2p_chunks": args.p2p_chunks or 1, "ipc_exchange": 1 if args.ipc_exchange else 0,
                     "multi_put": 0 if args.no_multi_put else 1, "staged_ctas": args.staged_ctas or 0,
-                    "self_first": 0}
+                    "self_first": 0, "oneside_self_ctas": 0,
+                    "remote_ctas": args.remote_ctas if args.remote_ctas is not None else -4}
         for mname, tun in variants:
             label = mname + "".join(f" {k}={v}" for k, v in tun.items())
             if mname == name and not tun:

@@ -678,7 +678,7 @@ static pa_status one_sided(Plan* P, Comm* comm, const void* src, void* dst, unsi
 
   // self block: fused K3 on the low-priority stream, beside the remote kernels
   if (timing) CU(cudaEventRecord(S.t[4], S.unpack_s));
-  RC(launch_block(P->self_fused, src, dst, S.unpack_s, nullptr));
+  RC(launch_block(P->self_fused, src, dst, S.unpack_s, nullptr, g_tun.oneside_self_ctas));
   CU(cudaEventRecord(S.ev_unpack_done, S.unpack_s));
   if (timing) CU(cudaEventRecord(S.t[5], S.unpack_s));
   if (timing) CU(cudaEventRecord(S.t[2], S.comm_s));

@@ -120,6 +120,63 @@ int main(void) {
         const int64_t I[3] = {i, j, k};
         if (g[off(py, n, I)] != val(i, j, k)) return 1;
       }
+  /* host chain: x -> y -> z on host arrays, two submits in flight (pa_host_chain_*) */
+  {
+    pa_plan* chain_plans[2] = {xy, yz};
+    pa_host_chain* hc = NULL;
+    CHECK(pa_host_chain_create(2, chain_plans, NULL, &hc));
+    double* g2 = (double*)malloc(sizeof(double) * N);
+    int64_t t0 = -1, t1 = -1;
+    CHECK(pa_host_chain_submit(hc, h, g, &t0));
+    CHECK(pa_host_chain_submit(hc, h, g2, &t1));
+    CHECK(pa_host_chain_wait(hc, t1));
+    CHECK(pa_host_chain_wait(hc, -1));
+    if (t0 != 0 || t1 != 1) return 1;
+    for (int64_t k = 0; k < n[2]; ++k)
+      for (int64_t j = 0; j < n[1]; ++j)
+        for (int64_t i = 0; i < n[0]; ++i) {
+          const int64_t I[3] = {i, j, k};
+          if (g[off(pz, n, I)] != val(i, j, k) || g2[off(pz, n, I)] != val(i, j, k)) return 1;
+        }
+    pa_host_chain_destroy(hc);
+    free(g2);
+  }
+  /* PencilIO layout: the file is the global array in the pencil's MEMORY order
+   * (mpi_io.jl:372-380): written from the device, checked byte for byte, read back */
+  {
+    const char* path = "/tmp/pa_c_harness.bin";
+    FILE* f = fopen(path, "wb");
+    if (!f) return 1;
+    fclose(f);
+    int64_t gbytes = 0;
+    CHECK(pa_io_sizes(peny, 0, NULL, 8, 0, &gbytes, NULL, NULL, NULL, NULL));
+    if (gbytes != (int64_t)sizeof(double) * N) return 1;
+    CHECK(pa_io_write(peny, 0, NULL, 8, 0, uy, path, 0));
+    f = fopen(path, "rb");
+    if (!f || fread(g, sizeof(double), (size_t)N, f) != (size_t)N) return 1;
+    fclose(f);
+    for (int64_t k = 0; k < n[2]; ++k)
+      for (int64_t j = 0; j < n[1]; ++j)
+        for (int64_t i = 0; i < n[0]; ++i) {
+          const int64_t I[3] = {i, j, k};
+          if (g[off(py, n, I)] != val(i, j, k)) return 1;  /* one rank: file == parent(uy) */
+        }
+    cudaMemset(uz, 0, sizeof(double) * N);
+    CHECK(pa_io_read(peny, 0, NULL, 8, 0, uz, path, 0));
+    cudaMemcpy(g, uz, sizeof(double) * N, cudaMemcpyDeviceToHost);
+    for (int64_t q = 0; q < N; ++q) {
+      double a;
+      cudaMemcpy(&a, (double*)uy + q, sizeof a, cudaMemcpyDeviceToHost);
+      if (memcmp(&a, &g[q], sizeof a) != 0) return 1;
+      q += 997;  /* sample */
+    }
+    remove(path);
+  }
+  /* the fused unpack+FFT is for ComplexF64 only: a Float64 plan must be refused, not computed */
+  if (pa_transpose(xy, NULL, ux, uy, PA_WAITALL | PA_FFT_FORWARD, NULL) != PA_EINVAL) {
+    fprintf(stderr, "PA_FFT_FORWARD on Float64 should be refused\n");
+    return 1;
+  }
   printf("C ABI harness OK: x->y->z bit-exact, %lld kernel launches\n", (long long)pa_launch_count());
   pa_plan_destroy(xy);
   pa_plan_destroy(yz);
