@@ -60,6 +60,7 @@ pa_status pa_set_tunable(const char* name, int64_t value) {
   else if (!strcmp(name, "small_block_bytes")) g_tun.small_block_bytes = value;
   else if (!strcmp(name, "transpose_y_fastest")) g_tun.transpose_y_fastest = (int)value;
   else if (!strcmp(name, "multi_put")) g_tun.multi_put = (int)value;
+  else if (!strcmp(name, "fft_lines")) g_tun.fft_lines = (int)value;
   else if (!strcmp(name, "oneside_self_ctas")) g_tun.oneside_self_ctas = (int)value;
   else if (!strcmp(name, "p2p_chunks")) g_tun.p2p_chunks = (int)value;
   else if (!strcmp(name, "staged_ctas")) g_tun.staged_ctas = (int)value;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
   // (measured on B200, profiles/r2_fused_fft.txt: a win for 1024-point lines -- one CTA
   //  per SM less bound by shared memory --, a loss for 512-point lines, where the radix-16
   //  butterfly's 126 registers cost the third resident CTA: 1.17 -> 1.45 ms at 512^3)
-  constexpr int LOGR1 = (LOGL == 10) ? (LOGL - LOGRS) : 0;
+  constexpr int LOGR1 = (C == 4 && LOGL > LOGRS) ? (LOGL - LOGRS) : 0;
   static_assert(LOGR1 == 0 || LOGL - LOGR1 == LOGRS, "first-pass stride must equal the sweep");
   const cplx* twp = p.tw;
   auto tw = [twp](int i) {
@@ -350,7 +350,9 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     cudaGetLastError();
     return PA_ENOMEM;
   }
-  const int C = fft_lines(logL);
+  // tunable "fft_lines" = 4: 4 lines per CTA also for 256- / 512-point lines (64-byte gathers,
+  // first pass of radix 4 / 8 in registers, half the shared memory per CTA)
+  const int C = (g_tun.fft_lines == 4 && logL >= 8) ? 4 : fft_lines(logL);
   p.tiles_x = (unsigned)((p.ex + C - 1) / C);
   unsigned long long grid = p.tiles_x;
   for (int i = 0; i < p.no; ++i) grid *= (unsigned long long)p.oe[i];
@@ -379,8 +381,8 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     case 5: launch(k_unpack_fft<5, 8>); break;
     case 6: launch(k_unpack_fft<6, 8>); break;
     case 7: launch(k_unpack_fft<7, 8>); break;
-    case 8: launch(k_unpack_fft<8, 8>); break;
-    case 9: launch(k_unpack_fft<9, 8>); break;
+    case 8: if (C == 4) launch(k_unpack_fft<8, 4>); else launch(k_unpack_fft<8, 8>); break;
+    case 9: if (C == 4) launch(k_unpack_fft<9, 4>); else launch(k_unpack_fft<9, 8>); break;
     default: launch(k_unpack_fft<10, 4>); break;
   }
   if (e != cudaSuccess) {

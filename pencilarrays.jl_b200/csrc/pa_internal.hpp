@@ -164,6 +164,7 @@ struct Tunables {
   int nccl_fences = 0;   // 1: one-sided paths fence with NCCL groups even when the flag window exists
   int oneside_self_ctas = 0;  // grid cap of the self block (K3) while the one-sided puts / gets run
                               // beside it (0 = uncapped, < 0 per SM): trades K3 speed for NVLink rate
+  int fft_lines = 0;     // fused unpack+FFT: 4 = four lines per CTA for 256/512-point lines too (default 8)
   int multi_put = 1;     // 1: one launch interleaving every peer's tiles (+ in-kernel flags) on the one-sided paths
   int p2p_chunks = 1;    // staged schedules: sub-blocks per peer block (pack-chunk -> send-chunk -> unpack-chunk)
   int self_first = 0;    // staged schedules: 1 = self block first and beside the packs (round-1 order)

@@ -58,8 +58,11 @@ def main():
             ms_f = timed(lambda: torch.fft.fft(dst.data, dim=-1, out=tmp))
             ms_tf = timed(lambda: (pa.transpose_(t), torch.fft.fft(dst.data, dim=-1, out=tmp)))
             ms_fused = timed(lambda: pa.transpose_(t, fft="forward"))
+            pa.set_tunable("fft_lines", 4)
+            ms_fused4 = timed(lambda: pa.transpose_(t, fft="forward"))
+            pa.set_tunable("fft_lines", 0)
             r = dict(dims=dims, leg=leg, L=L, transpose_ms=round(ms_t, 4), cufft_ms=round(ms_f, 4),
-                     unfused_ms=round(ms_tf, 4), fused_ms=round(ms_fused, 4),
+                     unfused_ms=round(ms_tf, 4), fused_ms=round(ms_fused, 4), fused_4lines_ms=round(ms_fused4, 4),
                      fused_frac_of_hbm=round(nb / ms_fused / 1e6 / PEAK, 3),
                      speedup_vs_unfused=round(ms_tf / ms_fused, 3))
             rows.append(r)
