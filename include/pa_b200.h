@@ -103,7 +103,10 @@ int pa_device_count(void);
  * "nccl_fences" = 1: one-sided methods fence with NCCL groups, "nccl_register"
  * (default 1; 0 = plain cudaMalloc arenas): staging arenas from ncclMemAlloc +
  * ncclCommRegister, "bulk_rows" = 1: row copies as the TMA bulk-copy pipeline,
- * "transpose_tbq" / "small_block_bytes": transpose tile shape,
+ * "transpose_tbq" (0/16 = 256-byte destination runs per tile, the default; 32 = 512),
+ * "transpose_y_fastest" (-1 = consecutive CTAs walk along the side with fewer tiles,
+ * the default; 0 / 1 = forced along source / destination rows), "small_block_bytes"
+ * (accepted, unused since round 2),
  * "multi_put" (default 1): the one-sided methods issue ONE launch over all peers'
  * blocks with the window protocol inside the kernel, "p2p_chunks" (default 1):
  * sub-blocks per peer block flowing pack -> exchange -> unpack independently
@@ -113,7 +116,13 @@ int pa_device_count(void);
  * "fence_timeout_ms" (default 60000): a flag wait longer than this records the
  * failure and traps, "pdl" (default 1): programmatic dependent launch between
  * back-to-back local kernels, "nccl_ctas": ncclCommInitRankConfig min/maxCTAs,
- * "host_chunk_bytes": bytes per pipelined cut of the host paths.                 */
+ * "host_chunk_bytes": bytes per pipelined cut of the host paths, "host_slots" (2..4):
+ * device staging sets = submits a pa_host_chain keeps in flight, "self_first" = 1:
+ * staged schedules run the self block first and beside the packs (round-1 order;
+ * default: remote packs first and alone), "oneside_self_ctas": grid cap of the self
+ * block while the one-sided puts run beside it (default 0 = uncapped, measured best),
+ * "fft_lines" = 4: the fused unpack+FFT uses four lines per CTA for 256/512-point
+ * lines too (default eight, measured faster).                                     */
 pa_status pa_set_tunable(const char* name, int64_t value);
 /* bind the calling thread to a device (one process per GPU: LOCAL_RANK).  All
  * handles created afterwards (streams, staging arenas, communicator) live there. */

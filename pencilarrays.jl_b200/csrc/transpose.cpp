@@ -1378,12 +1378,10 @@ pa_status host_chain_create(int n, Plan* const* plans, Comm* comm, HostChain** o
   c->comm = comm;
   c->cap = std::max<i64>(c->cap, 1);
   c->SLOTS = std::max(2, std::min(g_tun.host_slots, (int)HostChain::MAX_SLOTS));
-  HostChain* raw = c.get();
   auto fail = [&](pa_status s) {
     host_chain_destroy(c.release());
     return s;
   };
-  (void)raw;
   for (int s = 0; s < c->SLOTS; ++s)
     for (int k = 0; k < 2; ++k)
       if (cudaMalloc(&c->buf[s][k], (size_t)c->cap) != cudaSuccess) {
