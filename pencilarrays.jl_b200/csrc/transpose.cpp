@@ -662,16 +662,16 @@ static pa_status one_sided(Plan* P, Comm* comm, const void* src, void* dst, unsi
   const int nproc = P->nproc, me = P->self_index;
   const bool get = P->method == PA_PEER_GET;
   const bool timing = S.timing;
+  // (a rank none of whose peers owns anything has no window to register: nothing will be
+  //  put / got, but it still speaks the protocol)
   auto w = P->windows.find(get ? src : (const void*)dst);
-  if (w == P->windows.end()) {
-    set_error("one-sided transpose: `%s` has no registered window (pa_plan_set_window)",
-              get ? "src" : "dest");
-    return PA_ESTATE;
-  }
-  const std::vector<void*>& win = w->second;
+  const std::vector<void*> no_window(nproc, nullptr);
+  const std::vector<void*>& win = (w == P->windows.end()) ? no_window : w->second;
   for (int n = 0; n < nproc; ++n)
-    if (n != me && (get ? P->peers[n].recv_cnt : P->peers[n].send_cnt) > 0 && !win[n]) {
-      set_error("one-sided transpose: window of peer %d is missing", n + 1);
+    if (n != me && (get ? P->peers[n].recv_cnt : P->peers[n].send_cnt) > 0 &&
+        ((int)win.size() <= n || !win[n])) {
+      set_error("one-sided transpose: `%s` has no registered window for peer %d (pa_plan_set_window)",
+                get ? "src" : "dest", n + 1);
       return PA_ESTATE;
     }
   RC(check_fence_err(comm));

@@ -80,7 +80,13 @@ def main():
         comm = pa.Comm(dist.get_rank(), dist.get_world_size())
     rank, world = comm.rank, comm.size
     ran = 0
-    for case in CASES:
+    extra_cases = []
+    if mode != "gloo":
+        # seeded random configurations (tests/test_random_configs.py) with this world size:
+        # uneven / empty blocks, 2-d ... 4-d data, every permutation, 2 ... 16-byte elements
+        from test_random_configs import RANDOM_CASES
+        extra_cases = [dict(c, random=True) for c in RANDOM_CASES if math.prod(c["grid"]) == world][:6]
+    for case in CASES + extra_cases:
         if math.prod(case["grid"]) != world:
             continue
         ran += 1
@@ -107,6 +113,10 @@ def main():
         if mode == "nccl":  # the own-kernel exchange beside NCCL on the same communicator
             variants += [(pa.PointToPoint(), True, True, {"ipc_exchange": 1}),
                          (pa.Alltoallv(), True, True, {"ipc_exchange": 1, "p2p_chunks": 2})]
+        if case.get("random"):  # a shorter list: the point is the geometry, not the tunables
+            variants = [(pa.PointToPoint(), True, True, {}), (pa.Alltoallv(), True, True, {}),
+                        (pa.PeerPut(), True, True, {}), (pa.PeerGet(), True, False, {}),
+                        (pa.PointToPoint(), True, False, {"p2p_chunks": 3})]
         defaults = {"p2p_chunks": 1, "staged_ctas": 0, "multi_put": 1, "ipc_exchange": 0}
         if mode == "gloo":
             cur = cur_o[rank].data.reshape(-1, order="F").copy()
