@@ -783,14 +783,20 @@ def run_b200(args):
     dom = min(base.items(), key=lambda kv: kv[1]["GBps"]) if base else None
     rest = {k: v for k, v in kern.items() if not v.get("baseline_shape")}
     low = min(rest.items(), key=lambda kv: kv[1]["GBps"]) if rest else None
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            tj = json.load(f)
-            traffic = tj.get("bytes_per_launch")
-            traffic_src = {k: tj.get(k) for k in ("kernel", "file", "date", "algorithmic_bytes_per_launch")}
-    except Exception:
-        pass
+    def traffic_of(kernel_name):
+        """DRAM bytes per launch of that kernel from the committed ncu capture
+        (profiles/traffic.json, which names the file and the date); None when the selected
+        kernel has no capture."""
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tj = json.load(f)
+            for key, ent in tj.get("by_kernel", {}).items():
+                if key in kernel_name:
+                    return ent.get("bytes_per_launch"), {k: ent.get(k) for k in (
+                        "kernel", "file", "date", "algorithmic_bytes_per_launch")}
+        except Exception:
+            pass
+        return None, None
 
     # ---- BASELINE configs[1] beside it (N == 1): 256^3 Float64, 1 GPU, pack/unpack kernel only ----
     cfg1 = configs1_256cubed(pa, torch, peak) if (n == 1 and args.workload == "cfg4" and not args.quick) else None
@@ -916,8 +922,8 @@ def run_b200(args):
                             "last download, max over ranks"},
             "roofline": None if dom is None else {
                 "bound": "hbm", "kernel": dom[0], "achieved": dom[1]["GBps"], "peak": peak,
-                "unit": "GB/s", "frac": round(dom[1]["GBps"] / peak, 4), "traffic": traffic,
-                "traffic_source": traffic_src, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(dom[1]["GBps"] / peak, 4), "traffic": traffic_of(dom[0])[0],
+                "traffic_source": traffic_of(dom[0])[1], "peak_source": peak_src,
                 "alg_bytes_per_launch": dom[1]["alg_bytes"] // max(1, dom[1].get("launches", 1)),
                 "selection": "slowest of the BASELINE-shape kernels in `kernels` (K1 pack, K2 unpack, "
                              "K3 fused; configs[1], [3], [4])",
