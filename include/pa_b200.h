@@ -75,7 +75,10 @@ typedef enum pa_method {
  * `dst` receives fft(transposed array) (forward: exp(-2*pi*i*jk/n); backward: the
  * unnormalised inverse, as FFTW / PencilFFTs).  ComplexF64, power-of-two lines of
  * 8..1024 points, staged methods or local transposes, src and dst not aliased;
- * PA_EINVAL otherwise (transpose, then transform, separately).                       */
+ * PA_EINVAL otherwise (transpose, then transform, separately).  A plan between
+ * IDENTICAL pencils with src == dst is the plain in-place transform along the
+ * contiguous dim -- the first step of a PencilFFTs-style 3-d transform, whose other
+ * two steps are the fused transposes.                                               */
 #define PA_FFT_FORWARD  8u
 #define PA_FFT_BACKWARD 16u
 

@@ -48,6 +48,7 @@ struct FftBlock {
   const char* src;  // block origin
   int y0, ey;       // destination line range [y0, y0 + ey) this block fills
   long long ssy;    // source byte stride of the line dim
+  long long ssx;    // source byte stride between consecutive columns (= lines)
   long long so[FFT_MAXO];
 };
 struct FftParams {
@@ -59,6 +60,8 @@ struct FftParams {
   int no;
   long long oe[FFT_MAXO], dso[FFT_MAXO];
   int L, logL, sign, pitch;
+  int linear;  // the lines are contiguous in the source too (no transposition): consecutive
+               // threads then walk along a line instead of across the columns
   const cplx* tw;
   unsigned tiles_x;
 };
@@ -150,7 +153,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
     return cplx{w.x, w.y};
   };
   {
-    const int c = t % C, r = t / C;
+    // transposing gather: C consecutive threads read C consecutive columns of one source row;
+    // linear gather (lines contiguous in the source): consecutive threads read along a line
+    const int c = p.linear ? t / RS : t % C, r = p.linear ? t % RS : t / C;
     cplx* line = sm + c * pitch;
     if constexpr (LOGR1 > 0) {
       constexpr int R1 = 1 << LOGR1;
@@ -163,8 +168,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
 #pragma unroll
           for (int b = 0; b < FFT_MAXB; ++b)
             if (b < p.nb && y >= p.blk[b].y0 && y < p.blk[b].y0 + p.blk[b].ey)
-              s = p.blk[b].src + so_off[b] + (long long)(y - p.blk[b].y0) * p.blk[b].ssy;
-          v[q] = __ldcs(reinterpret_cast<const double2*>(s + (x0 + c) * (long long)sizeof(cplx)));
+              s = p.blk[b].src + so_off[b] + (long long)(y - p.blk[b].y0) * p.blk[b].ssy +
+                  (x0 + c) * p.blk[b].ssx;
+          v[q] = __ldcs(reinterpret_cast<const double2*>(s));
         }
         cplx a[R1];
 #pragma unroll
@@ -179,7 +185,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_unpack_fft(const __grid_constan
       for (int b = 0; b < FFT_MAXB; ++b) {
         if (b < p.nb) {
           const FftBlock& B = p.blk[b];
-          const char* s = B.src + so_off[b] + (x0 + c) * (long long)sizeof(cplx);
+          const char* s = B.src + so_off[b] + (x0 + c) * B.ssx;
           const int ey = B.ey, y0 = B.y0;
           const long long ssy = B.ssy;
           for (int y = r; y < ey; y += U * RS) {
@@ -263,10 +269,26 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     set_error("fused FFT: the destination has no contiguous dimension longer than 1");
     return PA_EINVAL;
   }
-  if (jy == 0) {
-    set_error("fused FFT: the transform axis is contiguous in the source too (no transposition "
-              "to fuse with); transform it in place instead");
-    return PA_EINVAL;
+  // jy == 0: the transform axis is contiguous in the source too -- no transposition along it
+  // (a local copy / permutation of the outer dims, or an in-place transform): the "columns"
+  // are then the next dim, and only a single block (the whole local array) is supported
+  const bool linear = (jy == 0);
+  int jx = 0;  // the column dim: consecutive lines of a CTA
+  if (linear) {
+    int nonempty = 0;
+    for (int b = 0; b < nb; ++b) nonempty += blocks[b]->count > 0;
+    if (nonempty > 1) {
+      set_error("fused FFT: the transform axis is contiguous in the source and the destination is "
+                "assembled from several blocks: transform after the transposition instead");
+      return PA_EINVAL;
+    }
+    jx = -1;
+    for (int b = 0; b < nb && jx < 0; ++b)
+      for (int i = 1; i < blocks[b]->nd_raw; ++i)
+        if (blocks[b]->raw[i].e > 1) {
+          jx = i;
+          break;
+        }
   }
   i64 min_doff = -1;
   const BlockCopy* ref = nullptr;
@@ -281,6 +303,7 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
       set_error("fused FFT: unexpected source layout");
       return PA_EINVAL;
     }
+    if (linear && B.raw[0].ds != 1) return PA_EINVAL;
     if (!ref) ref = &B;
     if (B.nd_raw != ref->nd_raw) return PA_EINVAL;
     for (int i = 0; i < B.nd_raw; ++i)
@@ -304,9 +327,10 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     F.y0 = (int)(B.dst_off - min_doff);
     F.ey = (int)B.raw[jy].e;
     F.ssy = B.raw[jy].ss * 16;
+    F.ssx = jx >= 0 ? B.raw[jx].ss * 16 : 16;
     int o = 0;
     for (int i = 1; i < B.nd_raw; ++i)
-      if (i != jy && B.raw[i].e > 1) F.so[o++] = B.raw[i].ss * 16;
+      if (i != jy && i != jx && B.raw[i].e > 1) F.so[o++] = B.raw[i].ss * 16;
     L += B.raw[jy].e;
   }
   int logL = 0;
@@ -330,11 +354,12 @@ pa_status unpack_fft(int nb, const BlockCopy* const* blocks, const void* const* 
     }
   }
   p.dst = (char*)dst + min_doff * 16;
-  p.ex = ref->raw[0].e;
-  p.dsx = ref->raw[0].ds * 16;
+  p.linear = linear ? 1 : 0;
+  p.ex = jx >= 0 ? ref->raw[jx].e : 1;
+  p.dsx = jx >= 0 ? ref->raw[jx].ds * 16 : 16;
   p.no = 0;
   for (int i = 1; i < ref->nd_raw; ++i)
-    if (i != jy && ref->raw[i].e > 1) {
+    if (i != jy && i != jx && ref->raw[i].e > 1) {
       if (p.no >= FFT_MAXO) return PA_EINVAL;
       p.oe[p.no] = ref->raw[i].e;
       p.dso[p.no] = ref->raw[i].ds * 16;

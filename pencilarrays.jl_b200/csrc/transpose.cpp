@@ -1086,9 +1086,13 @@ pa_status transpose(Plan* P, Comm* comm, const void* src, void* dst, unsigned fl
   if (timing) CU(cudaEventRecord(S.t[0], user));
 
   const int fft_sign = (flags & PA_FFT_FORWARD) ? -1 : ((flags & PA_FFT_BACKWARD) ? 1 : 0);
-  if (fft_sign && src && dst &&
+  // src and dst may not alias -- except for the plain in-place transform along the contiguous
+  // dim (same pencil on both sides, src == dst): a CTA reads its lines completely before it
+  // writes them back
+  const bool fft_in_place = fft_sign && src && src == dst && P->dim < 0 && P->same_perm;
+  if (fft_sign && !fft_in_place && src && dst &&
       (src == dst || ranges_overlap(src, P->length_in * ES, dst, P->length_out * ES))) {
-    set_error("fused FFT: src and dst must not alias");
+    set_error("fused FFT: src and dst must not alias (in place only between identical pencils)");
     return PA_EINVAL;
   }
   if (fft_sign && (P->dim < 0 || P->nproc == 1)) {

@@ -321,6 +321,14 @@ def transpose_(*args, method=None, waitall=True, overlap=True, stage_self=False,
 transpose_bang = transpose_
 
 
+def fft_(u: PencilArray, direction="forward"):
+    """In-place 1-d complex FFT of ``u`` along its contiguous (first memory) dimension: the
+    first step of a PencilFFTs-style 3-d transform (the other two are ``transpose_(t,
+    fft=...)``).  Same kernel as the fused unpack+FFT, without a transposition."""
+    t = Transposition(u, u)
+    return transpose_(t, fft=direction).Ao
+
+
 def transpose_host_(t: Transposition, host_src: torch.Tensor, host_dst: torch.Tensor):
     """``transpose!`` on HOST arrays through ``pa_transpose_host``: upload, kernels and
     download pipelined inside the library; returns when ``host_dst`` is valid.  Pin the

@@ -188,6 +188,26 @@ def main():
                             tol = 8 * np.finfo(np.float64).eps * np.log2(L) * np.abs(want_f).max()
                             assert np.abs(got - want_f).max() <= tol, \
                                 ("fft", case["name"], k, rank, method, direction)
+                    if ok_shape and k == 1 and len(case["chain"]) >= 3:
+                        # a whole distributed 3-d FFT, PencilFFTs-style: fft along x in place, then
+                        # x->y and y->z with the next transform fused into the unpack; every rank's
+                        # z-pencil array must be its part of numpy.fft.fftn of the global array
+                        ux = pa.PencilArray.undef(tdt, pens[0], *extra)
+                        ux.data.copy_(src.data)
+                        uy = pa.PencilArray.undef(tdt, pens[1], *extra)
+                        uz = pa.PencilArray.undef(tdt, pens[2], *extra)
+                        pa.fft_(ux, "forward")
+                        pa.transpose_(pa.Transposition(uy, ux, method=pa.PointToPoint()), fft="forward")
+                        pa.transpose_(pa.Transposition(uz, uy, method=pa.Alltoallv()), fft="forward")
+                        torch.cuda.synchronize()
+                        F = np.fft.fftn(G, axes=(0, 1, 2))
+                        Fb = np.ascontiguousarray(F.reshape(-1, order="F")).view(np.uint8) \
+                            .reshape(-1, 16).reshape(shape + (16,), order="F")
+                        want3 = O.scatter(Fb, opens[2], extra, dtype)[rank].data.reshape(-1, order="F")
+                        got3 = np.ascontiguousarray(uz.data.cpu().numpy()).reshape(-1)
+                        n3 = math.prod(case["dims"])
+                        tol3 = 8 * np.finfo(np.float64).eps * np.log2(n3) * np.abs(F).max()
+                        assert np.abs(got3 - want3).max() <= tol3, ("fft3d", case["name"], rank)
                 cur = nxt
             cur_o = nxt_o
         if mode != "gloo" and len(case["chain"]) >= 3 and not extra:

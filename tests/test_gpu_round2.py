@@ -279,10 +279,62 @@ def test_fused_fft_refusals():
     _, (fx, fy, fz) = _single_rank_chain((16, 32, 8), torch.float64, ((2, 1, 3), (3, 2, 1)))
     with pytest.raises(pa.ArgumentError):      # not ComplexF64
         pa.transpose_(pa.Transposition(fy, fx), fft="forward")
-    # same contiguous dim on both sides: nothing is transposed, nothing to fuse with
+    # a line length that is not a power of two (21) is refused whatever the layout
     topo = pa.MPITopology(pa.COMM_SELF, (1, 1))
-    px = pa.Pencil(topo, (16, 32, 8), (2, 3))
-    p2 = pa.Pencil(px, decomp_dims=(1, 3), permute=pa.Permutation(1, 3, 2))
-    a, b = pa.PencilArray.undef(torch.complex128, px), pa.PencilArray.undef(torch.complex128, p2)
+    px = pa.Pencil(topo, (21, 16, 8), (2, 3))
+    a = pa.PencilArray.undef(torch.complex128, px)
     with pytest.raises(pa.ArgumentError):
-        pa.transpose_(pa.Transposition(b, a), fft="forward")
+        pa.fft_(a, "forward")
+
+
+@pytest.mark.parametrize("dims", [(16, 8, 32), (64, 12, 8), (1024, 3, 5), (8, 8, 8)])
+def test_in_place_line_fft_and_local_permute_fft(dims):
+    """`fft_(u)`: the in-place transform along the contiguous dim (same kernel, linear
+    gather); and a local permutation that keeps the contiguous dim, transformed on the way."""
+    topo = pa.MPITopology(pa.COMM_SELF, (1, 1))
+    px = pa.Pencil(topo, dims, (2, 3))
+    u = pa.PencilArray.undef(torch.complex128, px)
+    u.data.view(torch.float64).normal_()
+    before = u.data.cpu().numpy()
+    L = dims[0]
+    n0 = pa.launch_count()
+    pa.fft_(u, "forward")
+    torch.cuda.synchronize()
+    assert pa.launch_count() - n0 == 1
+    ref = np.fft.fft(before, axis=-1)
+    tol = 8 * np.finfo(np.float64).eps * np.log2(L) * np.abs(ref).max()
+    assert np.abs(u.data.cpu().numpy() - ref).max() <= tol
+    pa.fft_(u, "backward")
+    torch.cuda.synchronize()
+    assert np.abs(u.data.cpu().numpy() / L - before).max() <= tol
+    # x stays contiguous, (y, z) swap places: permuted copy + transform in one kernel
+    p2 = pa.Pencil(px, decomp_dims=(2, 3), permute=pa.Permutation(1, 3, 2))
+    v = pa.PencilArray.undef(torch.complex128, p2)
+    pa.transpose_(pa.Transposition(v, u), fft="forward")
+    torch.cuda.synchronize()
+    ref2 = np.fft.fft(u.data.cpu().numpy(), axis=-1).transpose(1, 0, 2)  # torch dims (z,y,x)->(y,z,x)
+    assert np.abs(v.data.cpu().numpy() - ref2).max() <= 8 * np.finfo(np.float64).eps * np.log2(L) * np.abs(ref2).max()
+
+
+@pytest.mark.parametrize("dims", [(16, 32, 8), (64, 64, 64), (8, 128, 16)])
+def test_three_dimensional_fft_like_pencilffts(dims):
+    """fft along x in place, then x->y and y->z transposes with the next transform fused:
+    the z-pencil array, read in logical order, is numpy.fft.fftn of the input; the backward
+    chain returns N^3 times the input."""
+    _, (ux, uy, uz) = _single_rank_chain(dims, torch.complex128, ((2, 1, 3), (3, 2, 1)))
+    ux.data.view(torch.float64).normal_()
+    G = ux.logical().cpu().numpy().copy()
+    orig = ux.data.clone()
+    pa.fft_(ux, "forward")
+    pa.transpose_(pa.Transposition(uy, ux), fft="forward")
+    pa.transpose_(pa.Transposition(uz, uy), fft="forward")
+    torch.cuda.synchronize()
+    ref = np.fft.fftn(G)
+    n = math.prod(dims)
+    tol = 8 * np.finfo(np.float64).eps * np.log2(n) * np.abs(ref).max()
+    assert np.abs(uz.logical().cpu().numpy() - ref).max() <= tol
+    pa.fft_(uz, "backward")
+    pa.transpose_(pa.Transposition(uy, uz), fft="backward")
+    pa.transpose_(pa.Transposition(ux, uy), fft="backward")
+    torch.cuda.synchronize()
+    assert (ux.data / n - orig).abs().max().item() <= 8 * np.finfo(np.float64).eps * np.log2(n) * orig.abs().max().item()
