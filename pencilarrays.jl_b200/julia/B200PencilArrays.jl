@@ -242,6 +242,11 @@ function Transpositions.transpose!(t::DeviceTransposition; waitall = true, fft =
     t
 end
 
+# In-place 1-d FFT of `u` along its contiguous dimension (same kernel, no transposition): with
+# the two fused transposes this is a whole PencilFFTs-style 3-d transform in three kernels.
+fft_lines!(u::PencilArray{T,N,<:CuArray}; direction = :forward) where {T,N} =
+    (Transpositions.transpose!(Transposition(u, u); fft = direction); u)
+
 # ---- host arrays: a chain of transpositions on `Array`-backed data ------------------
 # pa_host_chain_*: one submit = upload, every transpose! on the device, download;
 # asynchronous, double-buffered (download of one submit || upload of the next).
