@@ -30,6 +30,11 @@
 #include <mutex>
 #include <vector>
 
+// twiddles: one table lookup per butterfly, the other powers by squaring / products (the
+// lookups share the load/store path with shared memory, the kernel's limiter)
+#ifndef PA_FFT_TWIDDLE_LOOKUPS
+#define PA_FFT_TWIDDLE_LOOKUPS 1
+#endif
 #include "fft_core.hpp"
 #include "pa_internal.hpp"
 

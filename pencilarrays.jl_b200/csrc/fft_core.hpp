@@ -167,6 +167,15 @@ PA_HD void dft16(cplx* a, int sign) {
 // step, 2 step, 4 step (and 8 step): the others are one or two complex products away
 template <int R, class Tw>
 PA_HD void butterfly_twiddles(cplx* w, int step, int L, int sign, const Tw& tw) {
+#if defined(PA_FFT_TWIDDLE_LOOKUPS) && PA_FFT_TWIDDLE_LOOKUPS == 1
+  // one table lookup per butterfly, the powers by squaring / products (<= 4 roundings
+  // more than a direct lookup: still far inside 8 eps log2(L))
+  w[1] = tw(step & (L - 1));
+  if (sign > 0) w[1].y = -w[1].y;
+  if (R > 2) w[2] = cmul(w[1], w[1]);
+  if (R > 4) w[4] = cmul(w[2], w[2]);
+  if (R > 8) w[8] = cmul(w[4], w[4]);
+#else
   w[1] = tw(step & (L - 1));
   if (R > 2) w[2] = tw((2 * step) & (L - 1));
   if (R > 4) w[4] = tw((4 * step) & (L - 1));
@@ -177,6 +186,7 @@ PA_HD void butterfly_twiddles(cplx* w, int step, int L, int sign, const Tw& tw) 
     if (R > 4) w[4].y = -w[4].y;
     if (R > 8) w[8].y = -w[8].y;
   }
+#endif
   if (R > 2) w[3] = cmul(w[1], w[2]);
   if (R > 4) {
     w[5] = cmul(w[4], w[1]);
