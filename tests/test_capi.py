@@ -178,3 +178,23 @@ def test_new_entry_points_refuse_without_gpu_or_bad_arguments():
         gb = C.c_int64()
         assert lib.pa_io_sizes(p._h, 0, None, 8, 0, C.byref(gb), None, None, None, None) == _lib.PA_OK
         assert gb.value == 4 * 4 * 4 * 8
+
+
+def test_pencil_constructors_and_repr_follow_the_reference_docs():
+    """docs/src/Pencils.md:84-170: default decomposition = the rightmost dims, the
+    constructor from an existing pencil, permutations, and the printed summary."""
+    topo = pa.MPITopology(pa.Comm(0, 32), (8, 4))
+    assert repr(topo) == "MPI topology: 2D decomposition (8×4 processes)"
+    pen = pa.Pencil(topo, (16, 32, 64))
+    want = ("Decomposition of 3D data\n    Data dimensions: (16, 32, 64)\n"
+            "    Decomposed dimensions: (2, 3)\n    Data permutation: NoPermutation()")
+    assert repr(pen).startswith(want)
+    pen13 = pa.Pencil(topo, (16, 32, 64), (1, 3))
+    pen_y = pa.Pencil(pen, decomp_dims=(1, 3))
+    assert pa.decomposition(pen13) == pa.decomposition(pen_y) == (1, 3)
+    assert pen_y.buffers()[:2] == pen.buffers()[:2]          # shares the staging arenas
+    permuted = pa.Pencil(topo, (16, 32, 64), permute=pa.Permutation(2, 3, 1))
+    assert "Data permutation: Permutation(2, 3, 1)" in repr(permuted)
+    assert pa.size_global(permuted, pa.MemoryOrder()) == (32, 64, 16)
+    # 32 ranks on 16x32x64 with decomposition (2,3): every rank holds (16, 4, 16)
+    assert pa.size_local(pen) == (16, 4, 16)
