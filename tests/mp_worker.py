@@ -32,7 +32,12 @@ from util import CASES, DTYPES, beq, perm_of, apply_block  # noqa: E402
 import math  # noqa: E402
 
 
-def gloo_transpose(plan, src, dtype, it, rank):
+def gloo_transpose(plan, src, dtype, it, rank, nparts=1):
+    """pack -> exchange -> unpack with the C planner's descriptors only; with nparts > 1
+    every block travels as `nparts` separately packed, sent, received and unpacked
+    pieces cut where `pa_plan_get_chunk` says (the chunked PointToPoint schedule)."""
+    import ctypes as C
+    from pencilarrays_b200._lib import lib, check, BlockDesc
     info = plan.info
     dst = np.zeros(max(1, info.length_out), dtype=dtype)
     if info.dim == 0:
@@ -41,30 +46,46 @@ def gloo_transpose(plan, src, dtype, it, rank):
     send = np.zeros(max(1, info.send_bytes // it), dtype=dtype)
     recv = np.zeros(max(1, info.recv_bytes // it), dtype=dtype)
     nproc, me = info.nproc, info.self_index
+
+    def chunk(op, p, c):
+        d, off, nb = BlockDesc(), C.c_int64(), C.c_int64()
+        check(lib.pa_plan_get_chunk(plan.h, op, p, c, nparts, C.byref(d), C.byref(off), C.byref(nb)))
+        return d, off.value, nb.value
+
     for p in range(1, nproc + 1):
         peer = plan.peer(p)
-        apply_block(plan.block(0, p), src, recv if peer.is_self else send)
+        if peer.is_self:
+            apply_block(plan.block(0, p), src, recv)
+        else:
+            for c in range(nparts):
+                apply_block(chunk(0, p, c)[0], src, send)
     reqs, keep = [], []
     for k in range(1, nproc):  # same rotation as the CUDA driver
-        to = plan.peer((me - 1 + k) % nproc + 1)
-        fr = plan.peer((me - 1 - k) % nproc + 1)
-        if to.send_count:
-            t = torch.from_numpy(send[to.send_offset // it:(to.send_offset + to.send_count) // it]
-                                 .view(np.uint8).copy())
-            keep.append(t)
-            reqs.append(dist.isend(t, to.world_rank))
-        if fr.recv_count:
-            t = torch.empty(fr.recv_count, dtype=torch.uint8)
-            keep.append((t, fr))
-            reqs.append(dist.irecv(t, fr.world_rank))
+        pt, pf = (me - 1 + k) % nproc + 1, (me - 1 - k) % nproc + 1
+        to, fr = plan.peer(pt), plan.peer(pf)
+        for c in range(nparts):
+            _, so, sn = chunk(0, pt, c)
+            _, ro, rn = chunk(1, pf, c)
+            if sn:
+                t = torch.from_numpy(send.view(np.uint8)[so:so + sn].copy())
+                keep.append(t)
+                reqs.append(dist.isend(t, to.world_rank, tag=c))
+            if rn:
+                t = torch.empty(rn, dtype=torch.uint8)
+                keep.append((t, ro))
+                reqs.append(dist.irecv(t, fr.world_rank, tag=c))
     for r in reqs:
         r.wait()
     for item in keep:
         if isinstance(item, tuple):
-            t, fr = item
-            recv[fr.recv_offset // it:(fr.recv_offset + fr.recv_count) // it] = t.numpy().view(dtype)
+            t, ro = item
+            recv.view(np.uint8)[ro:ro + t.numel()] = t.numpy()
     for p in range(1, nproc + 1):
-        apply_block(plan.block(1, p), recv, dst)
+        if plan.peer(p).is_self:
+            apply_block(plan.block(1, p), recv, dst)
+        else:
+            for c in range(nparts):
+                apply_block(chunk(1, p, c)[0], recv, dst)
     return dst
 
 
@@ -135,6 +156,8 @@ def main():
                 plan = _Plan(pens[k - 1], pens[k], extra, it, pa.PointToPoint())
                 got = gloo_transpose(plan, cur, dtype, it, rank)[:want.size]
                 assert beq(got, want), (case["name"], k, rank)
+                got3 = gloo_transpose(plan, cur, dtype, it, rank, nparts=3)[:want.size]
+                assert beq(got3, want), (case["name"], k, rank, "chunks=3")
                 cur = got
             else:
                 nxt = None
